@@ -1,0 +1,336 @@
+// api.cu -- the C ABI of include/kmpb200.h: context, pattern upload, the two count entry points.
+#include <algorithm>
+#include <new>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "kmpb_device.cuh"
+
+namespace {
+
+int use_device(const kmpb_ctx *ctx)
+{
+    KMPB_CUDA(cudaSetDevice(ctx->device));
+    return KMPB_OK;
+}
+
+bool device_is_sm100(int device)
+{
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return false;
+    return prop.major == 10; // the library carries sm_100a code only
+}
+
+// counts[i] (+)= sum over slots of uniq_counts[slot][pat_to_uniq[i]]
+__global__ void kmpb_expand_counts_kernel(const unsigned long long *__restrict__ uniq_counts, uint32_t n_uniq,
+                                          int n_slots, const uint32_t *__restrict__ pat_to_uniq, uint32_t n_pat,
+                                          unsigned long long *__restrict__ counts, int accumulate)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pat) return;
+    const uint32_t u = pat_to_uniq[i];
+    unsigned long long v = accumulate ? counts[i] : 0ull;
+    for (int s = 0; s < n_slots; s++) v += uniq_counts[(size_t)s * n_uniq + u];
+    counts[i] = v;
+}
+
+int run_engine(kmpb_ctx *ctx, const kmpb_batch &b, int slot, cudaStream_t stream)
+{
+    uint64_t *acc = ctx->d_uniq_counts + (size_t)slot * ctx->host.n_uniq;
+    if (ctx->engine == KMPB_ENGINE_PERPAT) return kmpb_launch_perpat(ctx, b, acc, stream);
+    return kmpb_launch_union(ctx, b, slot, acc, stream);
+}
+
+} // namespace
+
+extern "C" {
+
+int kmpb_device_count(void)
+{
+    int n = 0, usable = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (int d = 0; d < n; d++) usable += device_is_sm100(d) ? 1 : 0;
+    return usable;
+}
+
+int kmpb_create(kmpb_ctx **out, int device)
+{
+    if (out == nullptr) return kmpb_fail(KMPB_EINVAL, "kmpb_create: NULL out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return kmpb_fail(KMPB_ENODEVICE, "no CUDA device (%s); libkmpb200 has no CPU path",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return kmpb_fail(KMPB_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    if (!device_is_sm100(device))
+        return kmpb_fail(KMPB_ENODEVICE, "device %d is not compute capability 10.x; libkmpb200 carries sm_100a code only", device);
+    kmpb_ctx *ctx = new (std::nothrow) kmpb_ctx();
+    if (ctx == nullptr) return kmpb_fail(KMPB_ENOMEM, "out of memory");
+    ctx->device = device;
+    KMPB_CUDA(cudaSetDevice(device));
+    int v = 0;
+    KMPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    ctx->sm_count = v;
+    KMPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    ctx->smem_optin = (size_t)v;
+    KMPB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto &s : ctx->copy_stream) KMPB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) KMPB_CUDA(cudaEventCreate(&ev));
+    for (auto &ev : ctx->ev_kernel) KMPB_CUDA(cudaEventCreate(&ev));
+    *out = ctx;
+    return KMPB_OK;
+}
+
+void kmpb_destroy(kmpb_ctx *ctx)
+{
+    if (ctx == nullptr) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    kmpb_release_tables(ctx);
+    cudaFree(ctx->d_work);
+    cudaFree(ctx->d_items);
+    for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
+        cudaFree(ctx->d_stage_bytes[i]);
+        cudaFree(ctx->d_stage_off[i]);
+        if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
+    }
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev_kernel) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int kmpb_set_engine(kmpb_ctx *ctx, int engine)
+{
+    if (ctx == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL context");
+    if (engine != KMPB_ENGINE_AUTO && engine != KMPB_ENGINE_PERPAT && engine != KMPB_ENGINE_UNION)
+        return kmpb_fail(KMPB_EINVAL, "unknown engine %d", engine);
+    ctx->engine = engine;
+    return KMPB_OK;
+}
+
+int kmpb_get_device(const kmpb_ctx *ctx) { return ctx ? ctx->device : -1; }
+uint64_t *kmpb_device_counts(kmpb_ctx *ctx) { return ctx ? ctx->d_counts : nullptr; }
+uint32_t kmpb_pattern_count(const kmpb_ctx *ctx) { return ctx && ctx->have_tables ? ctx->host.n_pat : 0; }
+uint64_t kmpb_launch_count(const kmpb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int kmpb_set_profile(kmpb_ctx *ctx, int on)
+{
+    if (ctx == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL context");
+    ctx->profile = on != 0;
+    return KMPB_OK;
+}
+
+int kmpb_last_kernel_ms(kmpb_ctx *ctx, double *ms_out)
+{
+    if (ctx == nullptr || ms_out == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL argument");
+    if (!ctx->profile) return kmpb_fail(KMPB_ESTATE, "kmpb_set_profile(ctx, 1) first");
+    KMPB_CUDA(cudaSetDevice(ctx->device));
+    KMPB_CUDA(cudaEventSynchronize(ctx->ev_kernel[1]));
+    float ms = 0;
+    KMPB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_kernel[0], ctx->ev_kernel[1]));
+    *ms_out = ms;
+    return KMPB_OK;
+}
+
+int kmpb_last_timing(const kmpb_ctx *ctx, double *ms_out, int n)
+{
+    if (ctx == nullptr || ms_out == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL argument");
+    for (int i = 0; i < n && i < 2; i++) ms_out[i] = ctx->last_ms[i];
+    return KMPB_OK;
+}
+
+int kmpb_set_patterns(kmpb_ctx *ctx, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat)
+{
+    if (ctx == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL context");
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    kmpb_tables fresh;
+    rc = kmpb_tables_build(&fresh, blob, pat_off, n_pat);
+    if (rc) return rc;
+    KMPB_CUDA(cudaDeviceSynchronize());
+    kmpb_release_tables(ctx);
+    ctx->host = fresh;
+    ctx->have_tables = true;
+    rc = kmpb_upload_tables(ctx);
+    if (rc) kmpb_release_tables(ctx);
+    return rc;
+}
+
+int kmpb_get_prefix(kmpb_ctx *ctx, uint32_t pattern_index, int32_t *pi_out, uint32_t capacity)
+{
+    if (ctx == nullptr || pi_out == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL argument");
+    if (!ctx->have_tables) return kmpb_fail(KMPB_ESTATE, "kmpb_get_prefix before kmpb_set_patterns");
+    if (pattern_index >= ctx->host.n_pat) return kmpb_fail(KMPB_EINVAL, "pattern index %u out of range", pattern_index);
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    const uint32_t u = ctx->host.pat_to_uniq[pattern_index];
+    const uint32_t m = ctx->host.uniq_len[u];
+    if (capacity < m) return kmpb_fail(KMPB_EINVAL, "prefix buffer holds %u entries, pattern has %u", capacity, m);
+    KMPB_CUDA(cudaMemcpy(pi_out, ctx->dev.pi + ctx->host.uniq_off[u], m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return KMPB_OK;
+}
+
+// Device-resident batch with the byte span given by the caller: fully asynchronous.
+int kmpb_count_device_span(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_packets,
+                           uint64_t first_byte, uint64_t end_byte, uint64_t *d_counts, void *stream_v)
+{
+    if (ctx == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL context");
+    if (!ctx->have_tables) return kmpb_fail(KMPB_ESTATE, "count before kmpb_set_patterns");
+    if (ctx->host.n_pat == 0) return KMPB_OK;
+    if (d_counts == nullptr || (n_packets && (d_bytes == nullptr || d_offsets == nullptr)))
+        return kmpb_fail(KMPB_EINVAL, "NULL device pointer");
+    if (end_byte < first_byte) return kmpb_fail(KMPB_EINVAL, "offsets decrease");
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    if ((rc = kmpb_union_scratch(ctx, end_byte - first_byte))) return rc;
+    const uint32_t nu = ctx->host.n_uniq;
+    KMPB_CUDA(cudaMemsetAsync(ctx->d_uniq_counts, 0, (size_t)nu * sizeof(uint64_t), stream));
+    kmpb_batch b{d_bytes, 0, d_offsets, n_packets, first_byte, end_byte};
+    if ((rc = run_engine(ctx, b, 0, stream))) return rc;
+    kmpb_expand_counts_kernel<<<(ctx->host.n_pat + 255) / 256, 256, 0, stream>>>(
+        (const unsigned long long *)ctx->d_uniq_counts, nu, 1, ctx->dev.pat_to_uniq, ctx->host.n_pat,
+        (unsigned long long *)d_counts, 1);
+    ctx->launches++;
+    KMPB_CUDA(cudaGetLastError());
+    return KMPB_OK;
+}
+
+int kmpb_count_device(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_packets,
+                      uint64_t *d_counts, void *stream_v)
+{
+    if (ctx == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL context");
+    if (n_packets == 0) return KMPB_OK;
+    if (d_offsets == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL device pointer");
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    uint64_t span[2];
+    KMPB_CUDA(cudaMemcpyAsync(&span[0], d_offsets, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    KMPB_CUDA(cudaMemcpyAsync(&span[1], d_offsets + n_packets, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    KMPB_CUDA(cudaStreamSynchronize(stream));
+    return kmpb_count_device_span(ctx, d_bytes, d_offsets, n_packets, span[0], span[1], d_counts, stream_v);
+}
+
+// Host batch: chunks of whole packets are copied to per-stream staging buffers and matched there, so
+// the H2D copy of chunk c+1.. overlaps the kernels of chunk c (the MPI variant's Scatterv, done by
+// the copy engines instead of the network: mpi_dumping.c:161).
+int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, uint64_t n_packets,
+                    uint64_t *counts_out)
+{
+    if (ctx == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL context");
+    if (!ctx->have_tables) return kmpb_fail(KMPB_ESTATE, "count before kmpb_set_patterns");
+    const uint32_t n_pat = ctx->host.n_pat, nu = ctx->host.n_uniq;
+    if (n_pat == 0) return KMPB_OK;
+    if (counts_out == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL counts_out");
+    memset(counts_out, 0, (size_t)n_pat * sizeof(uint64_t));
+    if (n_packets == 0) return KMPB_OK;
+    if (bytes == nullptr || offsets == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL batch pointer");
+    for (uint64_t k = 0; k < n_packets; k += std::max<uint64_t>(1, n_packets / 64))
+        if (offsets[k + 1] < offsets[k]) return kmpb_fail(KMPB_EINVAL, "offsets decrease at packet %llu", (unsigned long long)k);
+    int rc = use_device(ctx);
+    if (rc) return rc;
+
+    // chunk plan: whole packets, ~chunk_bytes each
+    uint64_t chunk_bytes = 64ull << 20;
+    if (const char *env = getenv("KMPB_CHUNK_MB")) {
+        long mb = atol(env);
+        if (mb > 0) chunk_bytes = (uint64_t)mb << 20;
+    }
+    struct chunk { uint64_t k0, k1; };
+    std::vector<chunk> plan;
+    uint64_t max_bytes = 0, max_pkts = 0;
+    for (uint64_t k0 = 0; k0 < n_packets;) {
+        const uint64_t want = offsets[k0] + chunk_bytes;
+        uint64_t k1 = (uint64_t)(std::lower_bound(offsets + k0 + 1, offsets + n_packets, want) - offsets);
+        if (k1 > n_packets) k1 = n_packets;
+        k1 = std::min<uint64_t>(k1, k0 + ((1ull << 31) - 2));
+        plan.push_back({k0, k1});
+        const uint64_t base = offsets[k0] & ~511ull;
+        max_bytes = std::max(max_bytes, offsets[k1] - base);
+        max_pkts = std::max(max_pkts, k1 - k0);
+        k0 = k1;
+    }
+    const int n_slots = (int)std::min<size_t>(KMPB_COPY_STREAMS, plan.size());
+    // staging (grown on demand, kept for the next call)
+    if (max_bytes + 1024 > ctx->stage_bytes_cap || max_pkts + 1 > ctx->stage_off_cap) {
+        KMPB_CUDA(cudaDeviceSynchronize());
+        const size_t bcap = std::max<size_t>(ctx->stage_bytes_cap, (size_t)max_bytes + 1024);
+        const size_t ocap = std::max<size_t>(ctx->stage_off_cap, (size_t)max_pkts + 1);
+        for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
+            cudaFree(ctx->d_stage_bytes[i]); ctx->d_stage_bytes[i] = nullptr;
+            cudaFree(ctx->d_stage_off[i]); ctx->d_stage_off[i] = nullptr;
+        }
+        ctx->stage_bytes_cap = ctx->stage_off_cap = 0;
+        for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
+            KMPB_CUDA(cudaMalloc((void **)&ctx->d_stage_bytes[i], bcap));
+            KMPB_CUDA(cudaMemset(ctx->d_stage_bytes[i], 0, bcap));
+            KMPB_CUDA(cudaMalloc((void **)&ctx->d_stage_off[i], ocap * sizeof(uint64_t)));
+        }
+        ctx->stage_bytes_cap = bcap;
+        ctx->stage_off_cap = ocap;
+    }
+    if ((rc = kmpb_union_scratch(ctx, max_bytes))) return rc;
+
+    KMPB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    KMPB_CUDA(cudaMemsetAsync(ctx->d_uniq_counts, 0, (size_t)KMPB_COPY_STREAMS * nu * sizeof(uint64_t), ctx->stream));
+    KMPB_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    for (int s = 0; s < n_slots; s++) KMPB_CUDA(cudaStreamWaitEvent(ctx->copy_stream[s], ctx->ev[2], 0));
+    for (size_t c = 0; c < plan.size(); c++) {
+        const int slot = (int)(c % KMPB_COPY_STREAMS);
+        cudaStream_t s = ctx->copy_stream[slot];
+        const uint64_t k0 = plan[c].k0, k1 = plan[c].k1;
+        const uint64_t base = offsets[k0] & ~511ull;
+        KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_bytes[slot], bytes + base, offsets[k1] - base, cudaMemcpyHostToDevice, s));
+        KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_off[slot], offsets + k0, (k1 - k0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        kmpb_batch b{ctx->d_stage_bytes[slot], base, ctx->d_stage_off[slot], k1 - k0, offsets[k0], offsets[k1]};
+        if ((rc = run_engine(ctx, b, slot, s))) return rc;
+    }
+    for (int s = 0; s < n_slots; s++) {
+        KMPB_CUDA(cudaEventRecord(ctx->ev[3], ctx->copy_stream[s]));
+        KMPB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev[3], 0));
+    }
+    kmpb_expand_counts_kernel<<<(n_pat + 255) / 256, 256, 0, ctx->stream>>>(
+        (const unsigned long long *)ctx->d_uniq_counts, nu, KMPB_COPY_STREAMS, ctx->dev.pat_to_uniq, n_pat,
+        (unsigned long long *)ctx->d_counts, 0);
+    ctx->launches++;
+    KMPB_CUDA(cudaGetLastError());
+    KMPB_CUDA(cudaMemcpyAsync(counts_out, ctx->d_counts, (size_t)n_pat * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KMPB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    KMPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    KMPB_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->last_ms[0] = ms;
+    ctx->last_ms[1] = 0;
+    // device-side error flags of the union engine (oversized packets)
+    if (ctx->engine != KMPB_ENGINE_PERPAT && ctx->d_work) {
+        uint32_t work[KMPB_COPY_STREAMS * 4];
+        KMPB_CUDA(cudaMemcpy(work, ctx->d_work, sizeof work, cudaMemcpyDeviceToHost));
+        for (int s = 0; s < n_slots; s++)
+            if (work[s * 4 + 1]) return kmpb_fail(KMPB_ELIMIT, "a packet of 2 GiB or more is not supported");
+    }
+    return KMPB_OK;
+}
+
+void *kmpb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        kmpb_fail(KMPB_ENOMEM, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void kmpb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+} // extern "C"

@@ -1,0 +1,118 @@
+// perpat_kernel.cu -- the per-pattern engine (KMPB_ENGINE_PERPAT).
+//
+// This is the reference's packet x pattern double loop (serial.c:153-155) laid out the way
+// BASELINE.json's north_star prescribes: every distinct pattern has a byte-indexed KMP transition
+// DFA (built on the device, tables.cu) staged in shared memory; one warp takes one packet, cuts its
+// text into 32 chunks, and every lane walks its chunk once per pattern, starting (pattern_len-1)
+// bytes early so a match that straddles a chunk edge is seen by exactly one lane -- the one whose
+// chunk holds the match's LAST byte.  Per-pattern hits are summed across the warp with
+// __reduce_add_sync, accumulated in shared memory, and leave the block as one atomic per pattern.
+//
+// The payload is re-walked once per pattern, so this engine is bound by shared-memory lookups
+// (~P x 1.3 per byte), not by HBM; it exists as the literal form of the design, as an independent
+// on-device cross-check of the union engine, and for the DFA-shared-memory-pressure sweep
+// (BASELINE config 4).  Pattern sets whose DFAs exceed shared memory are processed in tiles, one
+// launch per tile.
+#include <algorithm>
+
+#include "kmpb_device.cuh"
+
+constexpr int PP_THREADS = 512;
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+kmpb_perpat_kernel(const uint8_t *__restrict__ bytes, uint64_t abs_base, const uint64_t *__restrict__ offsets,
+                   uint64_t n_packets, const uint8_t *__restrict__ dfa_all, const uint32_t *__restrict__ uniq_off,
+                   uint32_t u0, uint32_t u1, unsigned long long *__restrict__ uniq_counts)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t n_tile = u1 - u0;
+    uint32_t *s_counts = reinterpret_cast<uint32_t *>(smem);            // [n_tile]
+    uint32_t *s_off = s_counts + n_tile;                                 // [n_tile+1], relative to the tile
+    uint8_t *s_dfa = smem + ((8u * n_tile + 4u + 15u) & ~15u);           // tile's DFA rows, 256 B each
+
+    const uint32_t tile_base = uniq_off[u0];
+    for (uint32_t i = threadIdx.x; i <= n_tile; i += PP_THREADS) {
+        s_off[i] = uniq_off[u0 + i] - tile_base;
+        if (i < n_tile) s_counts[i] = 0;
+    }
+    {   // stage the DFA rows with 16-byte loads (rows are 256-byte multiples, 256-byte aligned)
+        const uint4 *src = reinterpret_cast<const uint4 *>(dfa_all + 256ull * tile_base);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_dfa);
+        const uint32_t n16 = (uniq_off[u1] - tile_base) * 16u;
+        for (uint32_t i = threadIdx.x; i < n16; i += PP_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (PP_THREADS / 32) + (threadIdx.x >> 5);
+    const uint64_t n_warps = (uint64_t)gridDim.x * (PP_THREADS / 32);
+
+    for (uint64_t k = warp; k < n_packets; k += n_warps) {
+        const uint64_t beg = offsets[k];
+        const uint32_t len = (uint32_t)(offsets[k + 1] - beg);
+        const uint8_t *text = bytes + (beg - abs_base);
+        // the text ends at the first NUL byte (strlen in kmp_matcher, serial.c:191)
+        uint32_t z = len;
+        for (uint32_t i = lane; i < len; i += 32)
+            if (text[i] == 0) { z = i; break; }
+        const uint32_t n = __reduce_min_sync(0xffffffffu, z);
+        if (n == 0) continue;
+        const uint32_t chunk = (n + 31) / 32;
+        const uint32_t a = lane * chunk;
+        const uint32_t stop = min(a + chunk, n);
+        for (uint32_t t = 0; t < n_tile; t++) {
+            const uint32_t m = s_off[t + 1] - s_off[t];
+            uint32_t hits = 0;
+            if (a < n && n >= m) { // "no point trying to match things", serial.c:193
+                const uint8_t *rows = s_dfa + 256u * s_off[t];
+                uint32_t state = 0;
+                for (uint32_t i = a >= m - 1 ? a - (m - 1) : 0; i < stop; i++) {
+                    const uint32_t e = rows[256u * state + text[i]];
+                    state = e & 0x7fu;
+                    hits += (e >> 7) & (uint32_t)(i >= a); // a hit belongs to the chunk holding its last byte
+                }
+            }
+            const uint32_t total = __reduce_add_sync(0xffffffffu, hits);
+            if (lane == 0 && total) atomicAdd(&s_counts[t], total);
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < n_tile; t += PP_THREADS)
+        if (s_counts[t]) atomicAdd(&uniq_counts[u0 + t], (unsigned long long)s_counts[t]);
+}
+
+int kmpb_launch_perpat(kmpb_ctx *ctx, const kmpb_batch &b, uint64_t *d_uniq_counts, cudaStream_t stream)
+{
+    const kmpb_tables &h = ctx->host;
+    if (h.n_uniq == 0 || b.n_packets == 0) return KMPB_OK;
+    const size_t budget = ctx->smem_optin;
+    if (!ctx->attr_perpat_set) {
+        KMPB_CUDA(cudaFuncSetAttribute(kmpb_perpat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        ctx->attr_perpat_set = true;
+    }
+    uint32_t u0 = 0;
+    while (u0 < h.n_uniq) {
+        // largest tile [u0, u1) whose counters + offsets + DFA rows fit
+        uint32_t u1 = u0;
+        size_t need = 0;
+        while (u1 < h.n_uniq) {
+            uint32_t nt = u1 + 1 - u0;
+            size_t want = ((8u * nt + 4u + 15u) & ~15u) + 256ull * (h.uniq_off[u1 + 1] - h.uniq_off[u0]);
+            if (want > budget) break;
+            need = want;
+            u1++;
+        }
+        if (u1 == u0) return kmpb_fail(KMPB_ELIMIT, "pattern %u does not fit in shared memory", u0);
+        uint64_t warps_wanted = b.n_packets;
+        int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count, (warps_wanted + PP_THREADS / 32 - 1) / (PP_THREADS / 32));
+        if (ctx->profile && u0 == 0) KMPB_CUDA(cudaEventRecord(ctx->ev_kernel[0], stream));
+        kmpb_perpat_kernel<<<grid, PP_THREADS, need, stream>>>(b.d_bytes, b.abs_base, b.d_offsets, b.n_packets,
+                                                               ctx->dev.perpat_dfa, ctx->dev.uniq_off, u0, u1,
+                                                               (unsigned long long *)d_uniq_counts);
+        ctx->launches++;
+        KMPB_CUDA(cudaGetLastError());
+        u0 = u1;
+    }
+    if (ctx->profile) KMPB_CUDA(cudaEventRecord(ctx->ev_kernel[1], stream));
+    return KMPB_OK;
+}

@@ -1,0 +1,331 @@
+/* automaton.c -- host-side table construction for a pattern set (runs once per kmpb_set_patterns).
+ *
+ * The reference keeps one KMP failure table per pattern (kmp_prefix, serial.c:217-238) and walks
+ * every payload once per pattern (serial.c:153-155).  Walking the payload P times cannot come near
+ * the HBM roofline, so the union engine merges the P KMP automata into one DFA over the trie of all
+ * pattern prefixes: state = longest suffix of the text read so far that is a prefix of some pattern
+ * -- for a single pattern this is exactly the automaton kmp_matcher steps through (j, with the drop
+ * to prefix[j-1] on mismatch or after a hit, serial.c:203-211).  A state reports every pattern that
+ * is a suffix of it, which is what makes the per-pattern counts independent and overlapping.
+ *
+ * On top of it sits a 4-byte-deep shift-and prefilter over 7 buckets of patterns (+1 bucket that
+ * detects NUL bytes): the device looks every payload byte up once in `filter` and only walks the DFA
+ * around the rare positions where some bucket's first bytes all agree.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "kmpb_internal.h"
+
+#define N_BUCKET 7        /* pattern buckets; bit 7 of every depth belongs to the NUL detector */
+#define FILTER_DEPTH 4
+#define TEXT_ALPHABET 96.0 /* cost model only: distinct byte values expected in payload text */
+#define DP_LIMIT 1024      /* above this many distinct patterns the bucket split is not optimised */
+
+/* ---- distinct patterns ------------------------------------------------------------------------ */
+
+typedef struct {
+    const uint8_t *p;
+    uint32_t len, index;
+} pat_ref;
+
+static int cmp_content(const void *a, const void *b)
+{
+    const pat_ref *x = a, *y = b;
+    uint32_t n = x->len < y->len ? x->len : y->len;
+    int c = memcmp(x->p, y->p, n);
+    if (c) return c;
+    if (x->len != y->len) return x->len < y->len ? -1 : 1;
+    return x->index < y->index ? -1 : (x->index > y->index);
+}
+
+/* order used for bucketing: by min(len, depth) first so short patterns (which leave the deeper
+ * filter stages open) share buckets, then by content so common prefixes sit together */
+static int cmp_bucket(const void *a, const void *b)
+{
+    const pat_ref *x = a, *y = b;
+    uint32_t kx = x->len < FILTER_DEPTH ? x->len : FILTER_DEPTH, ky = y->len < FILTER_DEPTH ? y->len : FILTER_DEPTH;
+    if (kx != ky) return kx < ky ? -1 : 1;
+    return cmp_content(a, b);
+}
+
+/* ---- prefilter -------------------------------------------------------------------------------- */
+
+typedef struct {
+    uint64_t set[FILTER_DEPTH][4]; /* byte values allowed at each depth */
+    int open[FILTER_DEPTH];        /* some pattern is shorter than depth+1: every byte passes */
+} bucket_sets;
+
+static void sets_add(bucket_sets *s, const pat_ref *r)
+{
+    for (uint32_t d = 0; d < FILTER_DEPTH; d++) {
+        if (d < r->len) s->set[d][r->p[d] >> 6] |= 1ull << (r->p[d] & 63);
+        else s->open[d] = 1;
+    }
+}
+
+static double sets_cost(const bucket_sets *s)
+{
+    double c = 1.0;
+    for (uint32_t d = 0; d < FILTER_DEPTH; d++) {
+        if (s->open[d]) continue;
+        int n = 0;
+        for (int w = 0; w < 4; w++) n += __builtin_popcountll(s->set[d][w]);
+        double f = n / TEXT_ALPHABET;
+        c *= f > 1.0 ? 1.0 : f;
+    }
+    return c;
+}
+
+/* Split the bucket-ordered patterns into <= N_BUCKET contiguous runs minimising the summed
+ * per-byte candidate probability.  cut[b]..cut[b+1] is bucket b. */
+static double split_buckets(const pat_ref *sorted, uint32_t n, uint32_t *cut)
+{
+    uint32_t nb = n < N_BUCKET ? n : N_BUCKET;
+    for (uint32_t b = 0; b <= N_BUCKET; b++) cut[b] = n;
+    cut[0] = 0;
+    if (n == 0) return 0.0;
+    if (n > DP_LIMIT) {
+        double total = 0;
+        for (uint32_t b = 0; b < nb; b++) {
+            cut[b] = (uint32_t)((uint64_t)n * b / nb);
+            uint32_t hi = (uint32_t)((uint64_t)n * (b + 1) / nb);
+            bucket_sets s;
+            memset(&s, 0, sizeof s);
+            for (uint32_t i = cut[b]; i < hi; i++) sets_add(&s, &sorted[i]);
+            total += sets_cost(&s);
+        }
+        return total;
+    }
+    /* cost[i*(n+1)+j] = cost of one bucket holding sorted[i..j) */
+    double *cost = malloc((size_t)(n + 1) * (n + 1) * sizeof *cost);
+    double *best = malloc((size_t)(nb + 1) * (n + 1) * sizeof *best);
+    uint32_t *from = malloc((size_t)(nb + 1) * (n + 1) * sizeof *from);
+    for (uint32_t i = 0; i < n; i++) {
+        bucket_sets s;
+        memset(&s, 0, sizeof s);
+        for (uint32_t j = i + 1; j <= n; j++) {
+            sets_add(&s, &sorted[j - 1]);
+            cost[(size_t)i * (n + 1) + j] = sets_cost(&s);
+        }
+    }
+    for (uint32_t j = 0; j <= n; j++) best[j] = j == 0 ? 0.0 : 1e300;
+    for (uint32_t k = 1; k <= nb; k++) {
+        double *cur = best + (size_t)k * (n + 1), *prev = best + (size_t)(k - 1) * (n + 1);
+        for (uint32_t j = 0; j <= n; j++) {
+            cur[j] = 1e300;
+            from[(size_t)k * (n + 1) + j] = 0;
+            for (uint32_t i = k - 1; i < j; i++) {
+                if (prev[i] >= 1e300) continue;
+                double c = prev[i] + cost[(size_t)i * (n + 1) + j];
+                if (c < cur[j]) {
+                    cur[j] = c;
+                    from[(size_t)k * (n + 1) + j] = i;
+                }
+            }
+        }
+    }
+    double total = best[(size_t)nb * (n + 1) + n];
+    uint32_t j = n;
+    for (uint32_t k = nb; k >= 1; k--) {
+        uint32_t i = from[(size_t)k * (n + 1) + j];
+        cut[k - 1] = i;
+        j = i;
+    }
+    free(cost);
+    free(best);
+    free(from);
+    return total;
+}
+
+static void build_filter(kmpb_tables *t, pat_ref *uniq)
+{
+    uint32_t cut[N_BUCKET + 1];
+    qsort(uniq, t->n_uniq, sizeof *uniq, cmp_bucket);
+    t->filter_fp_estimate = split_buckets(uniq, t->n_uniq, cut);
+    memset(t->filter, 0, sizeof t->filter);
+    for (uint32_t b = 0; b < N_BUCKET; b++) {
+        bucket_sets s;
+        memset(&s, 0, sizeof s);
+        if (cut[b] == cut[b + 1]) continue;
+        for (uint32_t i = cut[b]; i < cut[b + 1]; i++) sets_add(&s, &uniq[i]);
+        for (uint32_t c = 0; c < 256; c++)
+            for (uint32_t d = 0; d < FILTER_DEPTH; d++)
+                if (s.open[d] || (s.set[d][c >> 6] >> (c & 63) & 1)) t->filter[c] |= 1u << (8 * d + b);
+    }
+    /* bucket 7: stages 0..2 always pass, stage 3 passes on NUL only -> bit 31 of the running
+     * shift-and word is set exactly on a NUL byte */
+    for (uint32_t c = 0; c < 256; c++) t->filter[c] |= 0x00808080u;
+    t->filter[0] |= 0x80000000u;
+    t->bucket_of_uniq_valid = 1;
+}
+
+/* ---- union automaton -------------------------------------------------------------------------- */
+
+static int build_dfa(kmpb_tables *t)
+{
+    /* byte classes */
+    int used[256] = {0};
+    for (uint32_t i = 0; i < t->uniq_off[t->n_uniq]; i++) used[t->uniq_blob[i]] = 1;
+    t->n_class = 1;
+    for (int c = 0; c < 256; c++) t->byte_class[c] = used[c] ? (uint8_t)t->n_class++ : 0;
+    if (t->n_class > 256) { /* all 256 byte values used: cannot happen (no NUL), but keep u8 safe */
+        return kmpb_fail(KMPB_ELIMIT, "pattern set uses every byte value");
+    }
+    const uint32_t nc = t->n_class;
+    uint64_t max_state = (uint64_t)t->uniq_off[t->n_uniq] + 1;
+    if (max_state * nc >= (1ull << 31))
+        return kmpb_fail(KMPB_ELIMIT, "pattern set too large: %llu trie states x %u byte classes exceeds 2^31 table entries",
+                         (unsigned long long)max_state, nc);
+
+    uint32_t *next = calloc((size_t)max_state * nc, sizeof *next); /* 0 = no child yet (root is never a child) */
+    uint32_t *term = malloc((size_t)max_state * sizeof *term);     /* uniq id ending at the state, or ~0 */
+    uint32_t *fail = calloc((size_t)max_state, sizeof *fail);
+    uint32_t *queue = malloc((size_t)max_state * sizeof *queue);
+    uint32_t *n_out = calloc((size_t)max_state, sizeof *n_out);
+    if (!next || !term || !fail || !queue || !n_out) {
+        free(next); free(term); free(fail); free(queue); free(n_out);
+        return kmpb_fail(KMPB_ENOMEM, "out of memory building the union automaton");
+    }
+    memset(term, 0xff, (size_t)max_state * sizeof *term);
+
+    /* trie of all pattern prefixes */
+    uint32_t n_state = 1;
+    for (uint32_t u = 0; u < t->n_uniq; u++) {
+        uint32_t s = 0;
+        for (uint32_t i = t->uniq_off[u]; i < t->uniq_off[u + 1]; i++) {
+            uint32_t cls = t->byte_class[t->uniq_blob[i]];
+            if (next[(size_t)s * nc + cls] == 0) next[(size_t)s * nc + cls] = n_state++;
+            s = next[(size_t)s * nc + cls];
+        }
+        term[s] = u;
+    }
+
+    /* breadth-first: failure link of a child = where the parent's failure state goes on the same
+     * byte (the KMP "while j>0 && p[j]!=c: j=prefix[j-1]" loop, resolved once per (state, byte));
+     * missing edges are filled with the failure state's edge, turning the trie into a full DFA */
+    uint32_t head = 0, tail = 0;
+    for (uint32_t cls = 0; cls < nc; cls++)
+        if (next[cls]) queue[tail++] = next[cls]; /* depth-1 states fail to the root */
+    while (head < tail) {
+        uint32_t s = queue[head++];
+        n_out[s] = (term[s] != 0xffffffffu) + n_out[fail[s]];
+        for (uint32_t cls = 0; cls < nc; cls++) {
+            uint32_t child = next[(size_t)s * nc + cls], via = next[(size_t)fail[s] * nc + cls];
+            if (child) {
+                fail[child] = via;
+                queue[tail++] = child;
+            } else {
+                next[(size_t)s * nc + cls] = via;
+            }
+        }
+    }
+
+    /* outputs: own pattern first (the longest), then the failure chain's */
+    uint32_t *out_head = malloc(((size_t)n_state + 1) * sizeof *out_head);
+    uint64_t total_out = 0;
+    for (uint32_t s = 0; s < n_state; s++) total_out += n_out[s];
+    uint32_t *out_id = malloc((size_t)(total_out ? total_out : 1) * sizeof *out_id);
+    if (!out_head || !out_id || total_out >= (1ull << 32)) {
+        free(next); free(term); free(fail); free(queue); free(n_out); free(out_head); free(out_id);
+        return kmpb_fail(KMPB_ENOMEM, "out of memory building the output lists");
+    }
+    uint32_t at = 0;
+    for (uint32_t s = 0; s < n_state; s++) {
+        out_head[s] = at;
+        for (uint32_t v = s; v != 0; v = fail[v])
+            if (term[v] != 0xffffffffu) out_id[at++] = term[v];
+    }
+    out_head[n_state] = at;
+
+    /* "the target state reports something" flag in bit 31 */
+    for (size_t e = 0; e < (size_t)n_state * nc; e++) {
+        uint32_t target = next[e];
+        next[e] = target | (n_out[target] ? 0x80000000u : 0u);
+    }
+    uint32_t *shrunk = realloc(next, (size_t)n_state * nc * sizeof *next);
+    t->next = shrunk ? shrunk : next;
+    t->n_state = n_state;
+    t->out_head = out_head;
+    t->out_id = out_id;
+    free(term); free(fail); free(queue); free(n_out);
+    return KMPB_OK;
+}
+
+/* ---- entry points ----------------------------------------------------------------------------- */
+
+int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat)
+{
+    memset(t, 0, sizeof *t);
+    if (n_pat && (blob == NULL || pat_off == NULL)) return kmpb_fail(KMPB_EINVAL, "kmpb_set_patterns: NULL pattern data");
+    t->n_pat = n_pat;
+    pat_ref *refs = malloc(((size_t)n_pat + 1) * sizeof *refs);
+    t->pat_to_uniq = malloc(((size_t)n_pat + 1) * sizeof *t->pat_to_uniq);
+    if (!refs || !t->pat_to_uniq) { free(refs); kmpb_tables_free(t); return kmpb_fail(KMPB_ENOMEM, "out of memory"); }
+    uint64_t blob_len = 0;
+    for (uint32_t i = 0; i < n_pat; i++) {
+        if (pat_off[i + 1] < pat_off[i]) { free(refs); kmpb_tables_free(t); return kmpb_fail(KMPB_EINVAL, "pattern offsets decrease at %u", i); }
+        uint32_t len = pat_off[i + 1] - pat_off[i];
+        if (len == 0 || len > KMPB_MAX_PATTERN_LEN) {
+            free(refs); kmpb_tables_free(t);
+            return kmpb_fail(KMPB_EINVAL, "pattern %u has %u bytes; 1..%d allowed (serial.c:64)", i, len, KMPB_MAX_PATTERN_LEN);
+        }
+        if (memchr(blob + pat_off[i], 0, len)) {
+            free(refs); kmpb_tables_free(t);
+            return kmpb_fail(KMPB_EINVAL, "pattern %u contains a NUL byte", i);
+        }
+        refs[i].p = blob + pat_off[i];
+        refs[i].len = len;
+        refs[i].index = i;
+        blob_len += len;
+    }
+    /* distinct patterns, numbered in content order */
+    qsort(refs, n_pat, sizeof *refs, cmp_content);
+    t->uniq_off = malloc(((size_t)n_pat + 1) * sizeof *t->uniq_off);
+    t->uniq_len = malloc(((size_t)n_pat + 1) * sizeof *t->uniq_len);
+    t->uniq_blob = malloc(blob_len ? blob_len : 1);
+    pat_ref *uniq = malloc(((size_t)n_pat + 1) * sizeof *uniq);
+    if (!t->uniq_off || !t->uniq_len || !t->uniq_blob || !uniq) {
+        free(refs); free(uniq); kmpb_tables_free(t);
+        return kmpb_fail(KMPB_ENOMEM, "out of memory");
+    }
+    uint32_t nu = 0, at = 0;
+    t->min_len = n_pat ? KMPB_MAX_PATTERN_LEN : 0;
+    for (uint32_t i = 0; i < n_pat; i++) {
+        int same = i > 0 && refs[i].len == refs[i - 1].len && memcmp(refs[i].p, refs[i - 1].p, refs[i].len) == 0;
+        if (!same) {
+            t->uniq_off[nu] = at;
+            t->uniq_len[nu] = refs[i].len;
+            memcpy(t->uniq_blob + at, refs[i].p, refs[i].len);
+            uniq[nu].p = t->uniq_blob + at;
+            uniq[nu].len = refs[i].len;
+            uniq[nu].index = nu;
+            at += refs[i].len;
+            nu++;
+            if (refs[i].len > t->max_len) t->max_len = refs[i].len;
+            if (refs[i].len < t->min_len) t->min_len = refs[i].len;
+        }
+        t->pat_to_uniq[refs[i].index] = nu - 1;
+    }
+    t->uniq_off[nu] = at;
+    t->n_uniq = nu;
+    free(refs);
+
+    int rc = build_dfa(t);
+    if (rc == KMPB_OK) build_filter(t, uniq);
+    free(uniq);
+    if (rc != KMPB_OK) kmpb_tables_free(t);
+    return rc;
+}
+
+void kmpb_tables_free(kmpb_tables *t)
+{
+    free(t->pat_to_uniq);
+    free(t->uniq_len);
+    free(t->uniq_off);
+    free(t->uniq_blob);
+    free(t->next);
+    free(t->out_head);
+    free(t->out_id);
+    memset(t, 0, sizeof *t);
+}

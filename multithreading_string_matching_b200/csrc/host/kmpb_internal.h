@@ -1,0 +1,57 @@
+/* kmpb_internal.h -- declarations shared by the host (C) and device (CUDA) halves of libkmpb200. */
+#ifndef KMPB_INTERNAL_H
+#define KMPB_INTERNAL_H
+
+#include "kmpb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* errors.c: printf-style setter for the thread-local message behind kmpb_last_error(); returns code */
+int kmpb_fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+
+/* ------------------------------------------------------------------------------------------------
+ * automaton.c: everything the device needs to match a pattern set, built once per set on the host.
+ *
+ * Union automaton = the per-pattern KMP automata (serial.c:190-238) merged into one DFA over the
+ * trie of all pattern prefixes (for a single pattern it IS that pattern's KMP DFA).  Duplicate
+ * patterns share one "unique" id; counts are expanded back to file order at the end.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct kmpb_tables {
+    /* patterns */
+    uint32_t n_pat;          /* patterns in file order (duplicates included) */
+    uint32_t n_uniq;         /* distinct patterns */
+    uint32_t *pat_to_uniq;   /* [n_pat] */
+    uint32_t *uniq_len;      /* [n_uniq] */
+    uint32_t *uniq_off;      /* [n_uniq+1] into uniq_blob */
+    uint8_t *uniq_blob;
+    uint32_t max_len, min_len;
+
+    /* byte classes: bytes that occur in no pattern share class 0 */
+    uint32_t n_class;
+    uint8_t byte_class[256];
+
+    /* union DFA: next[state * n_class + class] = target state, bit 31 set when the target state
+     * reports at least one pattern */
+    uint32_t n_state;
+    uint32_t *next;          /* [n_state * n_class] */
+    /* outputs of state s: uniq ids out_id[out_head[s] .. out_head[s+1]), longest pattern first */
+    uint32_t *out_head;      /* [n_state+1] */
+    uint32_t *out_id;
+
+    /* shift-and prefilter (kernel B): for byte value c, filter[c] has bit (8*d + b) set when some
+     * pattern of bucket b has byte c at depth d (or is shorter than d+1 bytes); bucket 7 of depth 3
+     * is the NUL detector, buckets 7 of depths 0..2 are always set */
+    uint32_t filter[256];
+    uint32_t bucket_of_uniq_valid; /* 1 when filter[] is usable (n_uniq > 0) */
+    double filter_fp_estimate;     /* estimated candidate probability per text byte, uniform bytes */
+} kmpb_tables;
+
+int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat);
+void kmpb_tables_free(kmpb_tables *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

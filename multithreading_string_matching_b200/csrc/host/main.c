@@ -1,0 +1,146 @@
+/* main.c -- kmp_match: the reference's command line on a B200.
+ *
+ *   kmp_match <file.pcap> <string.txt> [udp|tcp]            serial.c:3,33-51
+ *   kmp_match <file.pcap> <string.txt> <n> [tcp|udp]        openmp_data.c:2,35-54; <n> = number of
+ *                                                           GPUs (the reference's thread count)
+ *
+ * stdout is the reference's, byte for byte (serial.c:163-169): header line, one "pattern: N times!"
+ * line per pattern with a non-zero count in file order, then "Elapsed time = %f seconds" -- the
+ * interval covers what serial.c's covers (read + extract + match, serial.c:110-111,159-160).
+ * Usage text goes to stdout with exit status 1 (serial.c:43,49); an unreadable strings file is
+ * perror("error opening file: ") + exit 1 (serial.c:60-63); an unreadable pcap is "error reading pcap
+ * file: ..." on stderr + exit 1 (serial.c:92-95).  Throughput figures go to stderr when KMPB_STATS=1.
+ *
+ * With <n> > 1 the packets are split as mpi_dumping.c:149-157 splits them over ranks, one host
+ * thread drives each GPU, and the per-pattern count vectors are summed (mpi_dumping.c:202).
+ */
+#include <errno.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include "kmpb200.h"
+
+static double now_seconds(void)
+{
+    struct timeval tv; /* gettimeofday like timer.h:31-35 */
+    gettimeofday(&tv, NULL);
+    return (double)tv.tv_sec + (double)tv.tv_usec / 1e6;
+}
+
+typedef struct {
+    int device;
+    const kmpb_patterns *pats;
+    const kmpb_csr *csr;
+    uint64_t first, count;
+    uint64_t *counts;
+    int rc;
+    char err[512];
+} shard_job;
+
+static void *run_shard(void *arg)
+{
+    shard_job *job = arg;
+    kmpb_ctx *ctx = NULL;
+    job->rc = kmpb_create(&ctx, job->device);
+    if (job->rc == 0) job->rc = kmpb_set_patterns(ctx, job->pats->blob, job->pats->pat_off, job->pats->n_pat);
+    if (job->rc == 0)
+        job->rc = kmpb_count_host(ctx, job->csr->bytes, job->csr->offsets + job->first, job->count, job->counts);
+    if (job->rc != 0) snprintf(job->err, sizeof job->err, "%s", kmpb_last_error());
+    kmpb_destroy(ctx);
+    return NULL;
+}
+
+int main(int argc, char **argv)
+{
+    int proto = KMPB_PROTO_UDP, n_gpus = 1, openmp_form = 0;
+    const char *prog = "./kmp_match";
+    if (argc >= 4 && strcmp(argv[3], "udp") != 0 && strcmp(argv[3], "tcp") != 0 && atoi(argv[3]) > 0) openmp_form = 1;
+    const char *usage_colon = openmp_form ? "USAGE: %s <file.pcap> <string.txt> gpu_number [tcp/udp]\n"
+                                          : "USAGE: %s <file.pcap> <string.txt> [tcp/udp]\n";
+    const char *usage_plain = openmp_form ? "USAGE %s <file.pcap> <string.txt> gpu_number [tcp/udp]\n"
+                                          : "USAGE %s <file.pcap> <string.txt> [tcp/udp]\n";
+    int type_arg = openmp_form ? 4 : 3;
+    if (argc < 3 || argc > type_arg + 1) {
+        printf(usage_colon, prog);
+        return 1;
+    }
+    if (openmp_form) n_gpus = atoi(argv[3]);
+    if (argc == type_arg + 1) {
+        if (strcmp(argv[type_arg], "udp") == 0) proto = KMPB_PROTO_UDP;
+        else if (strcmp(argv[type_arg], "tcp") == 0) proto = KMPB_PROTO_TCP;
+        else {
+            printf(usage_plain, prog);
+            return 1;
+        }
+    }
+
+    kmpb_patterns pats;
+    int rc = kmpb_load_patterns_file(argv[2], &pats);
+    if (rc == KMPB_EIO) {
+        perror("error opening file: ");
+        return 1;
+    }
+    if (rc != 0) {
+        fprintf(stderr, "error reading patterns: %s\n", kmpb_last_error());
+        return 1;
+    }
+
+    int available = kmpb_device_count();
+    if (available <= 0) {
+        fprintf(stderr, "error: no B200-class CUDA device available (this program has no CPU path)\n");
+        return 1;
+    }
+    if (n_gpus > available) n_gpus = available;
+
+    double start = now_seconds();
+    kmpb_csr csr;
+    rc = kmpb_load_pcap_csr(argv[1], proto, 1, &csr);
+    if (rc != 0) {
+        fprintf(stderr, "error reading pcap file: %s\n", kmpb_last_error());
+        return 1;
+    }
+
+    uint64_t *counts = calloc(pats.n_pat ? pats.n_pat : 1, sizeof *counts);
+    shard_job *jobs = calloc((size_t)n_gpus, sizeof *jobs);
+    pthread_t *threads = calloc((size_t)n_gpus, sizeof *threads);
+    for (int g = 0; g < n_gpus; g++) {
+        jobs[g].device = g;
+        jobs[g].pats = &pats;
+        jobs[g].csr = &csr;
+        kmpb_shard_range(csr.n_packets, (uint32_t)n_gpus, (uint32_t)g, &jobs[g].first, &jobs[g].count);
+        jobs[g].counts = calloc(pats.n_pat ? pats.n_pat : 1, sizeof(uint64_t));
+        if (g > 0) pthread_create(&threads[g], NULL, run_shard, &jobs[g]);
+    }
+    run_shard(&jobs[0]);
+    for (int g = 0; g < n_gpus; g++) {
+        if (g > 0) pthread_join(threads[g], NULL);
+        if (jobs[g].rc != 0) {
+            fprintf(stderr, "error: GPU %d: %s\n", g, jobs[g].err);
+            return 1;
+        }
+        for (uint32_t i = 0; i < pats.n_pat; i++) counts[i] += jobs[g].counts[i];
+    }
+    double finish = now_seconds();
+
+    kmpb_print_report(stdout, &pats, counts);
+    printf("Elapsed time = %f seconds\n", finish - start);
+
+    if (getenv("KMPB_STATS")) {
+        double s = finish - start;
+        fprintf(stderr, "kmp_match: %llu frames, %llu payloads, %llu payload bytes, %u patterns, %d GPU(s): "
+                        "%.3f GB/s, %.3f Mpackets/s end to end (file read + pack + H2D + match)\n",
+                (unsigned long long)csr.n_frames, (unsigned long long)csr.n_packets,
+                (unsigned long long)csr.total_bytes, pats.n_pat, n_gpus,
+                (double)csr.total_bytes / s / 1e9, (double)csr.n_packets / s / 1e6);
+    }
+    for (int g = 0; g < n_gpus; g++) free(jobs[g].counts);
+    free(jobs);
+    free(threads);
+    free(counts);
+    kmpb_free_csr(&csr);
+    kmpb_free_patterns(&pats);
+    return 0;
+}

@@ -186,11 +186,13 @@ int orc_load_pcap_csr(const char *path, int proto, unsigned char **bytes_out, ui
         unsigned char rh[16];
         size_t got = fread(rh, 1, 16, fp);
         if (got == 0) break;
-        if (got != 16) { rc = -3; break; }
+        /* a damaged tail makes pcap_next_ex return -1, which ends the reference's
+         * `while (... >= 0)` loop (serial.c:115) with the packets read so far */
+        if (got != 16) break;
         uint32_t caplen = rd32(rh + 8, swapped);
-        if (caplen > (64u << 20)) { rc = -3; break; }
+        if (caplen > (64u << 20)) break;
         if (caplen > frame_cap) frame = realloc(frame, frame_cap = caplen + (caplen >> 1));
-        if (fread(frame, 1, caplen, fp) != caplen) { rc = -3; break; }
+        if (fread(frame, 1, caplen, fp) != caplen) break;
         frames++;
         uint32_t poff = 0, plen = 0;
         int ok = proto == ORC_PROTO_TCP ? orc_tcp_payload(frame, caplen, &poff, &plen)

@@ -58,7 +58,8 @@ int orc_tcp_payload(const unsigned char *frame, uint32_t frame_len, uint32_t *of
 int orc_load_patterns(const char *path, unsigned char **blob, uint32_t **pat_off, uint32_t *n_pat);
 
 /* serial.c:91-141 ingest: classic pcap -> flat CSR of accepted payloads (bytes + n+1 offsets).
- * Returns 0; -1 cannot open; -2 not a classic pcap; -3 truncated record. *n_frames = records read. */
+ * Returns 0; -1 cannot open; -2 not a classic pcap.  A truncated trailing record ends the walk like
+ * the reference's `>= 0` loop does.  *n_frames = records read. */
 int orc_load_pcap_csr(const char *path, int proto, unsigned char **bytes, uint64_t **offsets,
                       uint64_t *n_packets, uint64_t *n_frames);
 

@@ -29,7 +29,8 @@ def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(HERE, "liboracle.so")
-        if not os.path.isfile(path):
+        src = os.path.join(HERE, "kmp_oracle.c")
+        if not os.path.isfile(path) or os.path.getmtime(path) < os.path.getmtime(src):
             build()
         L = ctypes.CDLL(path)
         L.orc_kmp_prefix.argtypes = [_u8p, ctypes.c_int, _i32p]

@@ -1,0 +1,109 @@
+/* test_tables.c -- CPU check of the host-built tables (csrc/host/automaton.c), no GPU involved.
+ *
+ * For seeded random pattern sets and texts it checks, against a naive overlapping counter:
+ *   1. walking the union DFA from the root reports exactly the naive per-pattern counts
+ *      (the property that makes the union automaton a drop-in for P independent kmp_matcher calls);
+ *   2. the shift-and prefilter never misses: for every true occurrence starting at s the filter word
+ *      after byte s+3 (text padded with zero bytes) has one of bits 24..30 set;
+ *   3. bit 31 of the filter word is set exactly on NUL bytes.
+ * Exit status 0 = all good.  Built and run by tests/test_host.py.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "kmpb_internal.h"
+
+static uint64_t rng_state = 0x1234567;
+static uint32_t rnd(void)
+{
+    rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17;
+    return (uint32_t)(rng_state >> 11);
+}
+
+static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int nul_every)
+{
+    int na = (int)strlen(alpha);
+    uint8_t *blob = malloc((size_t)n_pat * 99 + 1);
+    uint32_t *off = malloc(((size_t)n_pat + 1) * sizeof *off);
+    uint32_t at = 0;
+    for (int i = 0; i < n_pat; i++) {
+        off[i] = at;
+        int len = 1 + (int)(rnd() % (uint32_t)max_len);
+        if (i > 0 && rnd() % 7 == 0) { /* duplicate of an earlier pattern */
+            int j = (int)(rnd() % (uint32_t)i);
+            len = (int)(off[j + 1] - off[j]);
+            memcpy(blob + at, blob + off[j], (size_t)len);
+        } else {
+            for (int k = 0; k < len; k++) blob[at + k] = (uint8_t)alpha[rnd() % (uint32_t)na];
+        }
+        at += (uint32_t)len;
+    }
+    off[n_pat] = at;
+    uint8_t *text = calloc((size_t)text_len + 8, 1);
+    for (int i = 0; i < text_len; i++) text[i] = (nul_every && rnd() % (uint32_t)nul_every == 0) ? 0 : (uint8_t)alpha[rnd() % (uint32_t)na];
+    for (int r = 0; r < 4 && n_pat; r++) { /* plant some patterns so hits exist with large alphabets */
+        int p = (int)(rnd() % (uint32_t)n_pat), len = (int)(off[p + 1] - off[p]);
+        if (len < text_len) memcpy(text + rnd() % (uint32_t)(text_len - len), blob + off[p], (size_t)len);
+    }
+
+    kmpb_tables t;
+    if (kmpb_tables_build(&t, blob, off, (uint32_t)n_pat) != 0) { fprintf(stderr, "build failed: %s\n", kmpb_last_error()); return 1; }
+
+    /* 1. DFA counts (NULs are ordinary mismatching bytes here: class 0) */
+    uint64_t *got = calloc((size_t)t.n_uniq + 1, sizeof *got);
+    uint32_t state = 0;
+    for (int i = 0; i < text_len; i++) {
+        uint32_t e = t.next[(size_t)state * t.n_class + t.byte_class[text[i]]];
+        state = e & 0x7fffffffu;
+        if ((e >> 31) != (t.out_head[state + 1] > t.out_head[state])) { fprintf(stderr, "report flag wrong\n"); return 1; }
+        for (uint32_t o = t.out_head[state]; o < t.out_head[state + 1]; o++) got[t.out_id[o]]++;
+    }
+    int bad = 0;
+    for (int p = 0; p < n_pat; p++) {
+        int len = (int)(off[p + 1] - off[p]);
+        uint64_t want = 0;
+        for (int i = 0; i + len <= text_len; i++) want += memcmp(text + i, blob + off[p], (size_t)len) == 0;
+        uint32_t u = t.pat_to_uniq[p];
+        if (t.uniq_len[u] != (uint32_t)len || memcmp(t.uniq_blob + t.uniq_off[u], blob + off[p], (size_t)len)) { fprintf(stderr, "uniq map wrong\n"); return 1; }
+        if (got[u] != want) { fprintf(stderr, "pattern %d: dfa %llu naive %llu\n", p, (unsigned long long)got[u], (unsigned long long)want); bad = 1; }
+        /* 2. filter is a superset */
+        for (int s = 0; s + len <= text_len; s++) {
+            if (memcmp(text + s, blob + off[p], (size_t)len)) continue;
+            uint32_t S = 0x00808080u;
+            for (int k = 0; k < 4; k++) S = ((S << 8) | 0xffu) & t.filter[text[s + k]]; /* text is zero padded */
+            if (!(S & 0x7f000000u)) { fprintf(stderr, "filter missed pattern %d at %d\n", p, s); bad = 1; }
+        }
+    }
+    /* 3. NUL detector */
+    uint32_t S = 0x00808080u;
+    for (int i = 0; i < text_len; i++) {
+        S = ((S << 8) | 0xffu) & t.filter[text[i]];
+        if ((S >> 31) != (text[i] == 0)) { fprintf(stderr, "NUL bit wrong at %d\n", i); bad = 1; break; }
+    }
+    free(got); free(text); free(blob); free(off);
+    kmpb_tables_free(&t);
+    return bad;
+}
+
+int main(void)
+{
+    int bad = 0;
+    const char *alphas[] = {"ab", "abc", "abcdefghijklmnopqrstuvwxyz0123456789", "aA-_ .:/"};
+    for (int trial = 0; trial < 200 && !bad; trial++) {
+        int n_pat = (int[]){0, 1, 2, 5, 8, 30, 97, 300}[trial % 8];
+        int max_len = (int[]){1, 2, 3, 4, 5, 12, 40, 99}[(trial / 8) % 8];
+        bad |= run_case(n_pat, max_len, alphas[trial % 4], 50 + (int)(rnd() % 3000), trial % 3 == 0 ? 40 : 0);
+    }
+    /* limits */
+    kmpb_tables t;
+    uint8_t longpat[101]; uint32_t off2[2] = {0, 100};
+    memset(longpat, 'x', sizeof longpat);
+    if (kmpb_tables_build(&t, longpat, off2, 1) != KMPB_EINVAL) { fprintf(stderr, "100-byte pattern accepted\n"); bad = 1; }
+    off2[1] = 0;
+    if (kmpb_tables_build(&t, longpat, off2, 1) != KMPB_EINVAL) { fprintf(stderr, "empty pattern accepted\n"); bad = 1; }
+    longpat[1] = 0; off2[1] = 3;
+    if (kmpb_tables_build(&t, longpat, off2, 1) != KMPB_EINVAL) { fprintf(stderr, "NUL pattern accepted\n"); bad = 1; }
+    printf(bad ? "FAIL\n" : "OK\n");
+    return bad;
+}

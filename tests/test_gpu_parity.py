@@ -1,0 +1,273 @@
+"""Parity of the CUDA path (through the C ABI of libkmpb200.so) against the oracle and the golden
+vectors of the unmodified reference.  Bit-exact: these are integer counts.  Needs a B200."""
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import DATA, GOLDEN, ROOT, golden_runs
+
+import multithreading_string_matching_b200 as kmp
+
+pytestmark = pytest.mark.gpu
+ENGINES = ["union", "perpat"]
+
+
+@pytest.fixture(scope="module")
+def matchers():
+    ms = {e: kmp.Matcher(0, engine=e) for e in ENGINES}
+    yield ms
+    for m in ms.values():
+        m.close()
+
+
+@pytest.fixture(scope="module")
+def strings(strings_txt):
+    return kmp.load_patterns(strings_txt)
+
+
+def csr(packets):
+    offsets = np.zeros(len(packets) + 1, dtype=np.uint64)
+    if packets:
+        np.cumsum([len(p) for p in packets], out=offsets[1:])
+    return np.frombuffer(b"".join(packets) + b"\0" * 16, dtype=np.uint8)[: int(offsets[-1])], offsets
+
+
+def check_all(matchers, oracle, patterns, packets, engines=ENGINES, label=""):
+    data, offsets = csr(packets)
+    want = oracle.count_csr(data, offsets, patterns)
+    for e in engines:
+        m = matchers[e]
+        m.set_patterns(patterns)
+        got = m.count_host(data, offsets)
+        assert got == want, (label, e, [(p, g, w) for p, g, w in zip(patterns, got, want) if g != w][:8])
+    return want
+
+
+# ---- the reference's own fixtures ---------------------------------------------------------------
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("pcap,proto,expected", golden_runs(), ids=lambda v: v if isinstance(v, str) else "")
+def test_bundled_pcaps_bit_exact_vs_serial_c(matchers, strings, engine, pcap, proto, expected):
+    """BASELINE config 2: every bundled pcap, output text identical to serial.c's."""
+    m = matchers[engine]
+    m.set_patterns(strings)
+    counts = m.count_pcap(os.path.join(DATA, pcap + ".pcap"), proto, pinned=True)
+    assert kmp.format_report(strings, counts) == expected
+
+
+def test_cli_output_is_the_reference_output(strings):
+    exe = os.path.join(ROOT, "multithreading_string_matching_b200", "bin", "kmp_match")
+    for pcap, proto, expected in golden_runs():
+        for argv in ([proto], ["1", proto]) + ([[]] if proto == "udp" else []):
+            r = subprocess.run([exe, os.path.join(DATA, pcap + ".pcap"), os.path.join(DATA, "strings.txt"), *argv],
+                               capture_output=True)
+            assert r.returncode == 0, r.stderr
+            lines = r.stdout.splitlines(keepends=True)
+            assert lines[-1].startswith(b"Elapsed time = ") and lines[-1].endswith(b" seconds\n")
+            assert b"".join(lines[:-1]) == expected, (pcap, argv)
+
+
+def test_device_built_prefix_tables(matchers, oracle, strings):
+    """kmpb_get_prefix == kmp_prefix (serial.c:217-238): golden vectors + every strings.txt token."""
+    vectors = json.load(open(os.path.join(GOLDEN, "kmp_vectors.json")))["vectors"]
+    pats = [bytes.fromhex(v["pattern"]) for v in vectors]
+    m = matchers["union"]
+    m.set_patterns(pats)
+    for i, v in enumerate(vectors):
+        assert m.prefix(i) == v["pi"], pats[i]
+    m.set_patterns(strings)
+    for i, p in enumerate(strings):
+        assert m.prefix(i) == oracle.kmp_prefix(p)
+
+
+def test_reference_kmp_vectors(matchers):
+    """kmp_matcher (serial.c:190-215) golden vectors: each (text, pattern) pair as a 1-packet batch,
+    grouped by pattern set to keep the number of table builds small."""
+    vectors = json.load(open(os.path.join(GOLDEN, "kmp_vectors.json")))["vectors"]
+    for e in ENGINES:
+        m = matchers[e]
+        for lo in range(0, len(vectors), 50):
+            group = vectors[lo:lo + 50]
+            pats = [bytes.fromhex(v["pattern"]) for v in group]
+            m.set_patterns(pats)
+            data, offsets = csr([bytes.fromhex(v["text"]) for v in group])
+            # pattern i is only expected to match its own text; count it over that single packet
+            for i, v in enumerate(group):
+                one = m.count_host(data[int(offsets[i]):int(offsets[i + 1])], np.array([0, offsets[i + 1] - offsets[i]], dtype=np.uint64))
+                assert one[i] == v["count"], (e, pats[i])
+
+
+# ---- semantics ---------------------------------------------------------------------------------
+
+def test_semantics_overlap_nul_duplicates(matchers, oracle):
+    pats = [b"aa", b"ab", b"aa", b"a", b"aaaa", b"b"]
+    pkts = [b"aaaa", b"abab\0abab", b"\0aaaa", b"", b"a", b"aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaa", b"ba" * 300]
+    want = check_all(matchers, oracle, pats, pkts)
+    assert want[0] == want[2] == 3 + 39 and want[1] == 2 + 299
+
+
+def test_empty_inputs(matchers, oracle):
+    check_all(matchers, oracle, [b"x"], [])
+    check_all(matchers, oracle, [b"x"], [b"", b"", b""])
+    check_all(matchers, oracle, [], [b"abc"])
+    check_all(matchers, oracle, [b"abc"], [b"ab", b"c"])  # no match across packets
+
+
+def test_nul_at_every_position(matchers, oracle):
+    """first-NUL truncation for a NUL at every offset of a 3-row packet, followed by a
+    packet that must be unaffected."""
+    pats = [b"ab", b"b", b"abab", b"zz"]
+    base = (b"ab" * 700)[:1100]
+    pkts = []
+    for z in range(0, 1100, 7):
+        pkts.append(base[:z] + b"\0" + base[z + 1:])
+        pkts.append(b"abab")
+    check_all(matchers, oracle, pats, pkts)
+    pkts = [base[:z] + b"\0" + base[z + 1:] for z in list(range(0, 40)) + list(range(500, 530)) + list(range(1080, 1100))]
+    check_all(matchers, oracle, pats, pkts)
+
+
+def test_pattern_straddling_every_edge(matchers, oracle):
+    """A long self-overlapping pattern placed at every offset around 16-byte group edges, 512-byte row
+    edges and packet edges."""
+    pat = b"abcabcabcabcabcab"  # 17 bytes: always spans two groups
+    pats = [pat, b"abcab", b"bc", b"c", b"cabca"]
+    pkts = []
+    for start in list(range(0, 40)) + list(range(490, 530)) + list(range(1000, 1040)):
+        body = bytearray(b"." * 1100)
+        body[start:start + len(pat)] = pat
+        pkts.append(bytes(body[:1100]))
+    check_all(matchers, oracle, pats, pkts)
+    # shifting packet starts: lead packets of every length 0..40 move every later edge
+    for lead in range(0, 41, 3):
+        check_all(matchers, oracle, pats, [b"x" * lead] + pkts[:20], label="lead%d" % lead)
+
+
+def test_self_overlap_runs(matchers, oracle):
+    pats = [b"a", b"aa", b"aaa", b"a" * 16, b"a" * 17, b"a" * 99, b"rr", b"ara"]
+    pkts = [b"a" * n for n in (1, 2, 15, 16, 17, 98, 99, 100, 511, 512, 513, 2048)] + [b"ar" * 600, b"r" * 77]
+    check_all(matchers, oracle, pats, pkts)
+
+
+def test_pattern_lengths_1_to_99(matchers, oracle):
+    rng = random.Random(99)
+    alpha = b"abcd"
+    text = bytes(rng.choice(alpha) for _ in range(6000))
+    pats = [text[i * 50:i * 50 + n] for i, n in enumerate(range(1, 100))]
+    pkts = [text[:3000], text[3000:], text[100:160], text]
+    check_all(matchers, oracle, pats, pkts)
+
+
+def test_random_batches(matchers, oracle):
+    rng = random.Random(20241018)
+    lens = [0, 1, 2, 3, 15, 16, 17, 31, 33, 63, 64, 65, 127, 129, 511, 512, 513, 1400, 3000, 9000]
+    for trial in range(40):
+        alpha = [b"ab", b"abc\0", bytes(range(0x20, 0x7F)), bytes(range(0x20, 0x7F)) + b"\0\0", bytes(range(256))][trial % 5]
+        pat_alpha = bytes(b for b in alpha if b) or b"a"
+        n_pat = rng.choice([1, 2, 3, 7, 8, 20, 97, 200])
+        pats = [bytes(rng.choice(pat_alpha) for _ in range(rng.choice([1, 2, 2, 3, 3, 4, 5, 6, 8, 12, 20, 64])))
+                for _ in range(n_pat)]
+        n_pkt = rng.choice([1, 2, 5, 40, 300])
+        pkts = []
+        for _ in range(n_pkt):
+            n = rng.choice(lens)
+            body = bytearray(rng.choice(alpha) for _ in range(n))
+            for _ in range(rng.randint(0, 3)):
+                p = rng.choice(pats)
+                if len(p) <= n:
+                    at = rng.randrange(0, n - len(p) + 1)
+                    body[at:at + len(p)] = p
+            pkts.append(bytes(body))
+        engines = ENGINES if sum(map(len, pkts)) * n_pat < 3e7 else ["union"]
+        check_all(matchers, oracle, pats, pkts, engines=engines, label="trial%d" % trial)
+
+
+def test_many_small_packets_and_item_edges(matchers, oracle):
+    """Work items are ~128 KB runs of whole packets: cross many item edges with tiny and odd packets."""
+    rng = random.Random(5)
+    pats = [b"id", b"ack", b"http", b"content-list", b"NOTIFY", b"rr"]
+    pkts = []
+    for i in range(9000):
+        n = rng.choice([0, 1, 5, 16, 33, 64, 64, 64, 100, 200])
+        body = bytearray(rng.choice(b"idackhtpNOTIFYr-_cnsl \0") for _ in range(n))
+        pkts.append(bytes(body))
+    check_all(matchers, oracle, pats, pkts)
+    big = [bytes(rng.choice(b"idackhtp") for _ in range(300_000)) for _ in range(3)]  # packets larger than an item
+    check_all(matchers, oracle, pats, big + pkts[:100], engines=["union"])
+
+
+# ---- synthetic workloads of BASELINE.json ------------------------------------------------------
+
+def test_synthetic_device_resident_stream(matchers, oracle, strings):
+    """Config 3 shape at reduced size: generated on the device, identical bits on the host, union
+    engine vs oracle on a prefix, additivity over slices, and both engines agreeing on a sample."""
+    import torch
+
+    n = 200_000
+    synth = kmp.Synth(seed=0xB200, payload_len=1400, plants=2, plant_patterns=strings)
+    m = matchers["union"]
+    m.set_patterns(strings)
+    d_bytes = torch.zeros(n * 1400 + 64, dtype=torch.uint8, device="cuda:0")
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device="cuda:0")
+    synth.fill_device(m, 0, n, d_bytes.data_ptr(), d_off.data_ptr())
+    torch.cuda.synchronize()
+    hdata, hoff = synth.fill_host(0, 3000)
+    assert np.array_equal(d_bytes[: 3000 * 1400].cpu().numpy(), hdata)
+    assert np.array_equal(d_off[:3001].cpu().numpy().astype(np.uint64), hoff)
+
+    def device_counts(first, count):
+        d_counts = torch.zeros(len(strings), dtype=torch.int64, device="cuda:0")
+        m.count_device(d_bytes.data_ptr(), d_off.data_ptr() + 8 * first, count, d_counts.data_ptr())
+        m.count_device(d_bytes.data_ptr(), d_off.data_ptr() + 8 * first, count, d_counts.data_ptr(),
+                       span=(first * 1400, (first + count) * 1400))  # accumulates: x2
+        torch.cuda.synchronize()
+        c = d_counts.cpu().numpy()
+        assert (c % 2 == 0).all()
+        return (c // 2).tolist()
+
+    whole = device_counts(0, n)
+    assert device_counts(0, 3000) == oracle.count_csr(hdata, hoff, strings)
+    parts = [device_counts(a, b) for a, b in ((0, 70_001), (70_001, 59_999), (130_000, 70_000))]
+    assert whole == [sum(col) for col in zip(*parts)]
+    assert sum(whole) >= 2 * n * 0.9  # the planted tokens are found
+    p = matchers["perpat"]
+    p.set_patterns(strings)
+    sample, soff = synth.fill_host(150_000, 2000)
+    assert p.count_host(sample, soff) == m.count_host(sample, soff) == oracle.count_csr(sample, soff, strings)
+
+
+def test_mixed_length_stream_host_path(matchers, oracle, strings):
+    """Config 5 shape at reduced size through the host (pinned, chunked H2D) entry point."""
+    synth = kmp.Synth(seed=11, len_mode=1, plants=2, plant_patterns=strings)
+    data, off = synth.fill_host(0, 30_000)
+    m = matchers["union"]
+    m.set_patterns(strings)
+    want = oracle.count_csr(data, off, strings)
+    os.environ["KMPB_CHUNK_MB"] = "4"  # force many chunks through the stream pipeline
+    try:
+        assert m.count_host(data, off) == want
+    finally:
+        del os.environ["KMPB_CHUNK_MB"]
+    assert m.count_host(data, off) == want
+
+
+def test_pattern_sweep_shapes(matchers, oracle):
+    """Config 4 shape at reduced size: n patterns of one length over random [a-z0-9]-ish text."""
+    rng = random.Random(4)
+    alpha = b"abcdefghijklmnopqrstuvwxyz0123456789"
+    text_pk = [bytes(rng.choice(alpha) for _ in range(1400)) for _ in range(300)]
+    for n_pat, length in ((1, 4), (16, 8), (64, 16), (256, 4), (256, 64), (128, 32)):
+        pats = []
+        for i in range(n_pat):
+            src = rng.choice(text_pk)
+            at = rng.randrange(0, 1400 - length)
+            pats.append(src[at:at + length] if i % 2 else bytes(rng.choice(alpha) for _ in range(length)))
+        engines = ENGINES if n_pat * length <= 2048 else ["union"]
+        check_all(matchers, oracle, pats, text_pk, engines=engines, label="%dx%d" % (n_pat, length))
+    # the per-pattern engine tiles pattern sets whose DFAs exceed shared memory
+    pats = [bytes(rng.choice(alpha) for _ in range(64)) for _ in range(40)] + [text_pk[0][5:69]]
+    check_all(matchers, oracle, pats, text_pk[:40], engines=["perpat"], label="tiled")
