@@ -106,7 +106,8 @@ int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets
 /* Device form: d_bytes (16-byte aligned, readable up to total_bytes rounded up to 16) and d_offsets
  * are device memory on the context's GPU; d_counts[n_pat] (device, uint64) is ACCUMULATED into, so
  * a caller can sum several batches and all-reduce once (mpi_dumping.c:202).  Asynchronous on
- * `stream` (a cudaStream_t passed as void*, NULL = the context's own stream). */
+ * `stream` (a cudaStream_t passed as void*; NULL = CUDA's default stream, as in the runtime API).
+ * One device-form call may be in flight per context at a time (they share scratch buffers). */
 int kmpb_count_device(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets,
                       uint64_t n_packets, uint64_t *d_counts, void *stream);
 /* Same, for a caller that already knows first_byte = offsets[0] and end_byte = offsets[n_packets]:

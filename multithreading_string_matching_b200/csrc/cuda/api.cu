@@ -187,7 +187,7 @@ int kmpb_count_device_span(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t
     if (end_byte < first_byte) return kmpb_fail(KMPB_EINVAL, "offsets decrease");
     int rc = use_device(ctx);
     if (rc) return rc;
-    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t stream = (cudaStream_t)stream_v; // NULL is CUDA's default stream, as in the runtime API
     if ((rc = kmpb_union_scratch(ctx, end_byte - first_byte))) return rc;
     const uint32_t nu = ctx->host.n_uniq;
     KMPB_CUDA(cudaMemsetAsync(ctx->d_uniq_counts, 0, (size_t)nu * sizeof(uint64_t), stream));
@@ -209,7 +209,7 @@ int kmpb_count_device(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_o
     if (d_offsets == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL device pointer");
     int rc = use_device(ctx);
     if (rc) return rc;
-    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    cudaStream_t stream = (cudaStream_t)stream_v;
     uint64_t span[2];
     KMPB_CUDA(cudaMemcpyAsync(&span[0], d_offsets, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
     KMPB_CUDA(cudaMemcpyAsync(&span[1], d_offsets + n_packets, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));

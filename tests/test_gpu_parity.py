@@ -62,7 +62,7 @@ def test_bundled_pcaps_bit_exact_vs_serial_c(matchers, strings, engine, pcap, pr
 def test_cli_output_is_the_reference_output(strings):
     exe = os.path.join(ROOT, "multithreading_string_matching_b200", "bin", "kmp_match")
     for pcap, proto, expected in golden_runs():
-        for argv in ([proto], ["1", proto]) + ([[]] if proto == "udp" else []):
+        for argv in [[proto], ["1", proto]] + ([[]] if proto == "udp" else []):
             r = subprocess.run([exe, os.path.join(DATA, pcap + ".pcap"), os.path.join(DATA, "strings.txt"), *argv],
                                capture_output=True)
             assert r.returncode == 0, r.stderr
