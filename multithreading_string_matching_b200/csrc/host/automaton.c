@@ -201,6 +201,16 @@ static int build_dfa(kmpb_tables *t)
         term[s] = u;
     }
 
+    /* the bare trie (goto function only, 0 = no edge), kept for the device's start-anchored
+     * verification walk: bit 31 of an edge says a pattern ends at the child */
+    uint32_t *trie = malloc((size_t)n_state * nc * sizeof *trie);
+    if (!trie) {
+        free(next); free(term); free(fail); free(queue); free(n_out);
+        return kmpb_fail(KMPB_ENOMEM, "out of memory building the trie");
+    }
+    for (size_t e = 0; e < (size_t)n_state * nc; e++)
+        trie[e] = next[e] ? (next[e] | (term[next[e]] != 0xffffffffu ? 0x80000000u : 0u)) : 0u;
+
     /* breadth-first: failure link of a child = where the parent's failure state goes on the same
      * byte (the KMP "while j>0 && p[j]!=c: j=prefix[j-1]" loop, resolved once per (state, byte));
      * missing edges are filled with the failure state's edge, turning the trie into a full DFA */
@@ -227,7 +237,7 @@ static int build_dfa(kmpb_tables *t)
     for (uint32_t s = 0; s < n_state; s++) total_out += n_out[s];
     uint32_t *out_id = malloc((size_t)(total_out ? total_out : 1) * sizeof *out_id);
     if (!out_head || !out_id || total_out >= (1ull << 32)) {
-        free(next); free(term); free(fail); free(queue); free(n_out); free(out_head); free(out_id);
+        free(next); free(term); free(fail); free(queue); free(n_out); free(out_head); free(out_id); free(trie);
         return kmpb_fail(KMPB_ENOMEM, "out of memory building the output lists");
     }
     uint32_t at = 0;
@@ -248,7 +258,10 @@ static int build_dfa(kmpb_tables *t)
     t->n_state = n_state;
     t->out_head = out_head;
     t->out_id = out_id;
-    free(term); free(fail); free(queue); free(n_out);
+    t->trie = trie;
+    uint32_t *term_shrunk = realloc(term, (size_t)n_state * sizeof *term);
+    t->state_term = term_shrunk ? term_shrunk : term;
+    free(fail); free(queue); free(n_out);
     return KMPB_OK;
 }
 
@@ -325,6 +338,8 @@ void kmpb_tables_free(kmpb_tables *t)
     free(t->uniq_off);
     free(t->uniq_blob);
     free(t->next);
+    free(t->trie);
+    free(t->state_term);
     free(t->out_head);
     free(t->out_id);
     memset(t, 0, sizeof *t);

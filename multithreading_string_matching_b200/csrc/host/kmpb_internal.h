@@ -36,6 +36,10 @@ typedef struct kmpb_tables {
      * reports at least one pattern */
     uint32_t n_state;
     uint32_t *next;          /* [n_state * n_class] */
+    /* the same states as a bare trie: trie[state * n_class + class] = child (0 = none), bit 31 set when
+     * a pattern ends at the child; state_term[state] = that pattern's distinct id, or ~0 */
+    uint32_t *trie;          /* [n_state * n_class] */
+    uint32_t *state_term;    /* [n_state] */
     /* outputs of state s: uniq ids out_id[out_head[s] .. out_head[s+1]), longest pattern first */
     uint32_t *out_head;      /* [n_state+1] */
     uint32_t *out_id;

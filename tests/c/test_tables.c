@@ -60,6 +60,21 @@ static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int
         for (uint32_t o = t.out_head[state]; o < t.out_head[state + 1]; o++) got[t.out_id[o]]++;
     }
     int bad = 0;
+    /* 1b. the bare trie, walked from every start position, reports the same counts */
+    uint64_t *got_trie = calloc((size_t)t.n_uniq + 1, sizeof *got_trie);
+    for (int s = 0; s < text_len; s++) {
+        uint32_t node = 0;
+        for (int k = s; k < text_len; k++) {
+            uint32_t e = t.trie[(size_t)node * t.n_class + t.byte_class[text[k]]];
+            if (!e) break;
+            node = e & 0x7fffffffu;
+            if ((e >> 31) != (t.state_term[node] != 0xffffffffu)) { fprintf(stderr, "trie terminal flag wrong\n"); return 1; }
+            if (e >> 31) got_trie[t.state_term[node]]++;
+        }
+    }
+    for (uint32_t u = 0; u < t.n_uniq; u++)
+        if (got_trie[u] != got[u]) { fprintf(stderr, "uniq %u: trie %llu dfa %llu\n", u, (unsigned long long)got_trie[u], (unsigned long long)got[u]); bad = 1; }
+    free(got_trie);
     for (int p = 0; p < n_pat; p++) {
         int len = (int)(off[p + 1] - off[p]);
         uint64_t want = 0;
