@@ -7,10 +7,12 @@
 //  in flight ahead of the one being scanned.  Each lane pushes its 16 bytes (+3 bytes of lookahead
 //  from its neighbour, by shuffle) through a 4-byte-deep shift-and filter over 8 buckets:
 //      S = ((S << 8) | 0xff) & filter[byte]
-//  filter[] lives in shared memory in a bank-private layout (byte address = byte*256 + lane*4), so the
-//  one lookup per byte never bank-conflicts and its address is a single PRMT.  Bits 24..30 of S say
-//  "the last 4 bytes are the first 4 bytes (or all the bytes) of some pattern of bucket b"; bit 31
-//  says "this byte is NUL".
+//  filter[] lives in shared memory in a bank-private layout (byte address = byte*256 + lane*4) at a
+//  64 KB-aligned shared address, so the one lookup per byte never bank-conflicts and its complete
+//  address is a single PRMT of the text word with a per-lane constant.  The shift-or-0xff is one
+//  integer multiply-add (FMA pipe), the AND one LOP3 (ALU pipe).  Bits 24..30 of S say "the last 4
+//  bytes are the first 4 bytes (or all the bytes) of some pattern of bucket b"; bit 31 says "this
+//  byte is NUL".
 //
 //  SLOW PATH (rare).  Lanes whose 16 start positions raised a flag push their group into a per-warp
 //  shared-memory ring.  When 32 entries have gathered the warp drains them with every lane busy.
@@ -31,10 +33,16 @@
 
 #include "kmpb_device.cuh"
 
-constexpr int UN_THREADS = 1024; // one block per SM
+#ifndef KMPB_UN_THREADS
+#define KMPB_UN_THREADS 768
+#endif
+#ifndef KMPB_UN_ITEM_KB
+#define KMPB_UN_ITEM_KB 64
+#endif
+constexpr int UN_THREADS = KMPB_UN_THREADS; // one block per SM; 768 = 24 warps, up to 85 registers per thread
 constexpr int UN_WARPS = UN_THREADS / 32;
 constexpr uint32_t UN_ROW = 512;             // bytes per warp row
-constexpr uint32_t UN_ITEM_BYTES = 32 << 10; // target work-item size
+constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item size
 constexpr uint32_t UN_QCAP = 64;             // ring entries per warp and kind
 constexpr uint32_t UN_QS_WORDS = 8;          // simple entry: 16 B group, 4 B lookahead, group index, pad
 constexpr uint32_t UN_QC_WORDS = 4;          // complex entry: group index, zone|dead, first/last packet of the item
@@ -42,7 +50,15 @@ constexpr uint32_t UN_LUT_BYTES = 256 * 256; // 256-byte row per byte value; lan
 constexpr uint32_t UN_NOBOUND = 0xffffffffu;
 constexpr uint32_t FULL = 0xffffffffu;
 
-constexpr size_t UN_SMEM_FIXED = UN_LUT_BYTES + 256 + (size_t)UN_WARPS * UN_QCAP * (UN_QS_WORDS + UN_QC_WORDS) * 4;
+// Dynamic shared memory.  The LUT must start at a 64 KB-aligned shared address; the gap in front of it
+// (63 KB when the dynamic window starts at 0x400, the usual case) holds the simple rings, the byte
+// classes and the counters, the complex rings follow the LUT.  If the gap is too small for them they
+// go behind the complex rings instead; 64 KB + LUT + complex rings covers both layouts, and keeps
+// ~70 KB of the SM's 228 KB as L1 for the trie / automaton tables of the slow path.
+constexpr uint32_t UN_QS_BYTES = UN_WARPS * UN_QCAP * UN_QS_WORDS * 4;
+constexpr uint32_t UN_QC_BYTES = UN_WARPS * UN_QCAP * UN_QC_WORDS * 4;
+constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_QC_BYTES;
+constexpr uint32_t UN_SMEM_COUNTS_MAX = (65536 - UN_QS_BYTES - 256) / 4 - 64; // distinct patterns counted in shared memory
 
 struct union_params {
     const uint8_t *bytes; // device pointer to absolute byte abs_base (abs_base % 512 == 0)
@@ -62,6 +78,8 @@ struct union_params {
     const uint8_t *byte_class;
     uint32_t n_class, n_uniq, max_len;
     uint32_t counts_in_smem;
+    uint32_t mul256; // the value 256, passed at run time so the shift-or-0xff compiles to an integer
+                     // multiply-add on the FMA pipe instead of competing for the ALU pipe
     unsigned long long *uniq_counts;
 };
 
@@ -85,6 +103,20 @@ __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets
 }
 
 // ---- helpers -----------------------------------------------------------------------------------
+// streaming 16-byte load: read once, keep it out of L1 (which holds the slow path's tables)
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
 // 0x80 in every byte of w that is zero (exact, no false positives above a zero byte)
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t w)
 {
@@ -98,6 +130,8 @@ __device__ __forceinline__ uint32_t zero_mask16(const uint4 &v)
     return pack4(zero_bytes(v.x)) | pack4(zero_bytes(v.y)) << 4 | pack4(zero_bytes(v.z)) << 8 |
            pack4(zero_bytes(v.w)) << 12;
 }
+// mask of lanes >= l (l may be 32)
+__device__ __forceinline__ uint32_t lanes_ge(uint32_t l) { return l >= 32 ? 0u : ~((1u << l) - 1u); }
 
 __device__ __forceinline__ void count_hit(const union_params &p, uint32_t *s_counts, uint32_t u)
 {
@@ -105,60 +139,68 @@ __device__ __forceinline__ void count_hit(const union_params &p, uint32_t *s_cou
     else atomicAdd(p.uniq_counts + u, 1ull);
 }
 
-#define LUT_AT(word, sel) (*reinterpret_cast<const uint32_t *>(lut + __byte_perm((word), laneoff, (sel))))
-#define SA_STEP(word, sel, acc)                \
-    do {                                       \
-        const uint32_t m_ = LUT_AT(word, sel); \
-        S = ((S << 8) | 0xffu) & m_;           \
-        acc |= S;                              \
+// filter word of byte `sel` of `word`: the PRMT builds the whole shared address
+// [lutlane.b0 | byte | lutlane.b2 | lutlane.b3], lutlane = 64 KB-aligned LUT base + 4*lane
+#define LUT_AT(word, sel) lds32(__byte_perm((word), lutlane, (sel)))
+#define SEL0 0x7604
+#define SEL1 0x7614
+#define SEL2 0x7624
+#define SEL3 0x7634
+#define SA_NEXT(word, sel) (S = (S * mul + 255u) & LUT_AT(word, sel))
+#define SA_STEP(word, sel, acc) \
+    do {                        \
+        SA_NEXT(word, sel);     \
+        acc |= S;               \
     } while (0)
-#define SA_WORD(word, acc)          \
-    do {                            \
-        SA_STEP(word, 0x5504, acc); \
-        SA_STEP(word, 0x5514, acc); \
-        SA_STEP(word, 0x5524, acc); \
-        SA_STEP(word, 0x5534, acc); \
+#define SA_WORD(word, acc)        \
+    do {                          \
+        SA_STEP(word, SEL0, acc); \
+        SA_STEP(word, SEL1, acc); \
+        SA_STEP(word, SEL2, acc); \
+        SA_STEP(word, SEL3, acc); \
     } while (0)
 // same step, recording in bit `bit` of cm whether a candidate start fired
-#define SV_STEP(word, sel, bit)                              \
-    do {                                                     \
-        const uint32_t m_ = LUT_AT(word, sel);               \
-        S = ((S << 8) | 0xffu) & m_;                         \
-        cm |= (S & 0x7f000000u) ? (1u << (bit)) : 0u;        \
+#define SV_STEP(word, sel, bit)                       \
+    do {                                              \
+        SA_NEXT(word, sel);                           \
+        cm |= (S & 0x7f000000u) ? (1u << (bit)) : 0u; \
     } while (0)
 
 // Slow path, simple entry: the group's 16 bytes + 4 bytes of lookahead sit in shared memory at
 // `entry`; no packet boundary lies within reach of a match starting in the group and no NUL precedes
 // the group in its packet.  Start-anchored trie walk from every start position that fired.
-__device__ __noinline__ void verify_simple(const union_params &p, const uint8_t *lut, const uint8_t *s_class,
-                                           uint32_t *s_counts, const uint32_t *entry, uint32_t laneoff)
+__device__ __noinline__ void verify_simple(const union_params &p, const uint8_t *s_class, uint32_t *s_counts,
+                                           const uint32_t *entry, uint32_t lutlane, uint32_t mul)
 {
     const uint4 v = *reinterpret_cast<const uint4 *>(entry);
     const uint32_t la = entry[4], g16 = entry[5];
     uint32_t S, cm = 0;
-    S = LUT_AT(v.x, 0x5504) & 0x808080ffu;
-    S = ((S << 8) | 0xffu) & LUT_AT(v.x, 0x5514);
-    S = ((S << 8) | 0xffu) & LUT_AT(v.x, 0x5524);
-    SV_STEP(v.x, 0x5534, 0);
-    SV_STEP(v.y, 0x5504, 1); SV_STEP(v.y, 0x5514, 2); SV_STEP(v.y, 0x5524, 3); SV_STEP(v.y, 0x5534, 4);
-    SV_STEP(v.z, 0x5504, 5); SV_STEP(v.z, 0x5514, 6); SV_STEP(v.z, 0x5524, 7); SV_STEP(v.z, 0x5534, 8);
-    SV_STEP(v.w, 0x5504, 9); SV_STEP(v.w, 0x5514, 10); SV_STEP(v.w, 0x5524, 11); SV_STEP(v.w, 0x5534, 12);
-    SV_STEP(la, 0x5504, 13); SV_STEP(la, 0x5514, 14); SV_STEP(la, 0x5524, 15);
+    S = LUT_AT(v.x, SEL0) & 0x808080ffu;
+    SA_NEXT(v.x, SEL1);
+    SA_NEXT(v.x, SEL2);
+    SV_STEP(v.x, SEL3, 0);
+    SV_STEP(v.y, SEL0, 1); SV_STEP(v.y, SEL1, 2); SV_STEP(v.y, SEL2, 3); SV_STEP(v.y, SEL3, 4);
+    SV_STEP(v.z, SEL0, 5); SV_STEP(v.z, SEL1, 6); SV_STEP(v.z, SEL2, 7); SV_STEP(v.z, SEL3, 8);
+    SV_STEP(v.w, SEL0, 9); SV_STEP(v.w, SEL1, 10); SV_STEP(v.w, SEL2, 11); SV_STEP(v.w, SEL3, 12);
+    SV_STEP(la, SEL0, 13); SV_STEP(la, SEL1, 14); SV_STEP(la, SEL2, 15);
     // starts at or after the group's first NUL are dead (serial.c:191)
     const uint32_t zm = zero_mask16(v);
     if (zm) cm &= (1u << (__ffs(zm) - 1)) - 1u;
     const uint8_t *eb = reinterpret_cast<const uint8_t *>(entry);
     const uint8_t *gb = p.bytes + 16ull * g16;
+    const uint32_t *trie = p.trie;
+    const uint32_t *term = p.state_term;
+    const uint32_t ncls = p.n_class;
     while (cm) {
         const uint32_t i = __ffs(cm) - 1;
         cm &= cm - 1;
         uint32_t node = 0;
         for (uint32_t k = i;; k++) {
             const uint32_t c = k < 20 ? eb[k] : gb[k];
-            const uint32_t e = __ldg(p.trie + node * p.n_class + s_class[c]);
+            const uint32_t e = __ldg(trie + node * ncls + s_class[c]);
             if (e == 0) break;
             node = e & 0x7fffffffu;
-            if (e >> 31) count_hit(p, s_counts, __ldg(p.state_term + node));
+            if (e >> 31) count_hit(p, s_counts, __ldg(term + node));
         }
     }
 }
@@ -208,172 +250,236 @@ __device__ __noinline__ void verify_complex(const union_params &p, const uint8_t
     }
 }
 
+// per-warp streaming state
+struct warp_state {
+    // item
+    const uint8_t *text;  // byte 0 of the item's first row
+    const uint64_t *off;  // item boundary j is off[j] - row0
+    uint64_t row0;
+    uint32_t nbound, e_rel, load_end, g16_0, ks, ke;
+    // zone tracking (warp-uniform): zone = boundaries crossed so far; 0 = before the first packet
+    uint32_t zone, nb, nb_next;
+    bool dead;
+    // rings
+    uint32_t qs_head, qs_tail, qc_head, qc_tail;
+};
+
 __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_constant__ union_params p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *lut = smem;
-    uint8_t *s_class = smem + UN_LUT_BYTES;
-    uint32_t *qs_all = reinterpret_cast<uint32_t *>(smem + UN_LUT_BYTES + 256);
-    uint32_t *qc_all = qs_all + UN_WARPS * UN_QCAP * UN_QS_WORDS;
-    uint32_t *s_counts = p.counts_in_smem ? qc_all + UN_WARPS * UN_QCAP * UN_QC_WORDS : nullptr;
+    __shared__ uint32_t s_lut_saddr;
+    // the LUT sits at the first 64 KB-aligned shared address inside the dynamic allocation
+    const uint32_t dyn_saddr = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t lut_off = (0x10000u - (dyn_saddr & 0xffffu)) & 0xffffu;
+    uint8_t *lut = smem + lut_off;
+    uint32_t *qc_all = reinterpret_cast<uint32_t *>(lut + UN_LUT_BYTES);
+    const uint32_t front_bytes = UN_QS_BYTES + 256 + (p.counts_in_smem ? 4u * p.n_uniq : 0u);
+    uint8_t *front = lut_off >= front_bytes ? smem : lut + UN_LUT_BYTES + UN_QC_BYTES;
+    uint32_t *qs_all = reinterpret_cast<uint32_t *>(front);
+    uint8_t *s_class = front + UN_QS_BYTES;
+    uint32_t *s_counts = p.counts_in_smem ? reinterpret_cast<uint32_t *>(s_class + 256) : nullptr;
 
     for (uint32_t i = threadIdx.x; i < 256 * 32; i += UN_THREADS)
         reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + (i & 31)] = p.filter[i >> 5];
     for (uint32_t i = threadIdx.x; i < 256; i += UN_THREADS) s_class[i] = p.byte_class[i];
     if (s_counts)
         for (uint32_t i = threadIdx.x; i < p.n_uniq; i += UN_THREADS) s_counts[i] = 0;
+    if (threadIdx.x == 0) s_lut_saddr = dyn_saddr + lut_off;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t laneoff = lane << 2;
+    // read back through shared memory so that no LUT load can be scheduled above the barrier
+    const uint32_t lutlane = s_lut_saddr + (lane << 2);
+    const uint32_t mul = p.mul256;
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t *qs = qs_all + (threadIdx.x >> 5) * (UN_QCAP * UN_QS_WORDS);
     uint32_t *qc = qc_all + (threadIdx.x >> 5) * (UN_QCAP * UN_QC_WORDS);
-    uint32_t qs_head = 0, qs_tail = 0, qc_head = 0, qc_tail = 0; // ring counters (warp-uniform)
     const uint32_t reach = 15u + p.max_len;
+    warp_state w;
+    w.qs_head = w.qs_tail = w.qc_head = w.qc_tail = 0;
+
+    // one 512-byte row: `cur` is scanned, `nxt` supplies lane 31's lookahead
+    auto scan_row = [&](const uint4 &cur, const uint4 &nxt, const uint32_t row, const uint32_t g) {
+        // 3 bytes of lookahead: first word of the next group (next lane, or lane 0 of the next row)
+        const uint32_t la = __shfl_sync(FULL, lane == 0 ? nxt.x : cur.x, (lane + 1) & 31);
+
+        // ---- shift-and filter over 19 bytes ------------------------------------------------------
+        uint32_t S, accA, accB, accC;
+        S = LUT_AT(cur.x, SEL0) & 0x808080ffu; // no history: only the NUL stage is pre-armed
+        accA = S;
+        SA_STEP(cur.x, SEL1, accA);
+        SA_STEP(cur.x, SEL2, accA);
+        accB = 0;
+        SA_STEP(cur.x, SEL3, accB);
+        SA_WORD(cur.y, accB);
+        SA_WORD(cur.z, accB);
+        SA_WORD(cur.w, accB);
+        accC = 0;
+        SA_STEP(la, SEL0, accC);
+        SA_STEP(la, SEL1, accC);
+        SA_STEP(la, SEL2, accC);
+        const bool nul = ((accA | accB) >> 31) != 0;          // a NUL among my 16 bytes
+        const bool cand = ((accB | accC) & 0x7f000000u) != 0; // a candidate start among my 16 positions
+        const uint32_t nulm = __ballot_sync(FULL, nul);
+        const uint32_t candm = __ballot_sync(FULL, cand);
+
+        // ---- which lanes push, and into which ring ------------------------------------------------
+        const uint32_t row_end = row + UN_ROW;
+        uint32_t ms, mc;          // lanes pushing a simple / complex entry
+        uint32_t kz = w.zone;     // zone of my group's first byte
+        bool d0 = false;          // my packet already saw a NUL before my group
+        if (w.nb >= row_end) {    // no packet boundary inside this row: everything is warp-uniform
+            const uint32_t low = nulm & (0u - nulm);
+            const uint32_t deadm = w.dead ? FULL : (nulm ? ~((low << 1) - 1u) : 0u); // lanes above the first NUL lane
+            const uint32_t alive = candm & ~deadm;
+            // lanes whose reach (group start + 15 + longest pattern) crosses the next boundary
+            const uint32_t nearm = w.nb == UN_NOBOUND ? 0u : lanes_ge(((w.nb - reach - row) >> 4) + 1u);
+            ms = alive & ~nearm;
+            mc = alive & nearm;
+            w.dead = w.dead || nulm != 0;
+        } else {
+            const uint32_t zm = zero_mask16(cur);
+            uint32_t bin = 0, bat = 0; // lanes with a boundary inside their group / exactly at its start
+            uint32_t endm = 0;         // lanes past the item's last packet
+            uint32_t my_ob = 0, my_nb = UN_NOBOUND;
+            bool ended = false;
+            while (w.nb < row_end) {
+                const uint32_t lb = (w.nb - row) >> 4, ob = (w.nb - row) & 15u;
+                if (w.nb <= g) kz++;
+                else if (my_nb == UN_NOBOUND) my_nb = w.nb;
+                if (ob) {
+                    bin |= 1u << lb;
+                    if (lane == lb) my_ob = ob;
+                } else {
+                    bat |= 1u << lb;
+                }
+                w.zone++;
+                if (w.zone > w.nbound) { // past the item's last packet
+                    endm = ob ? ~((2u << lb) - 1u) : ~((1u << lb) - 1u);
+                    ended = true;
+                    w.nb = UN_NOBOUND;
+                    break;
+                }
+                w.nb = w.nb_next;
+                w.nb_next = w.zone + 1 <= w.nbound ? (uint32_t)(w.off[w.zone + 1] - w.row0) : UN_NOBOUND;
+            }
+            if (my_nb == UN_NOBOUND) my_nb = w.nb;
+            // lanes whose group has a NUL after its last inner boundary
+            const uint32_t nafter = __ballot_sync(FULL, my_ob != 0 && (zm >> my_ob) != 0);
+            const uint32_t before = (bin & lt) | (bat & (lt | (1u << lane))); // boundaries at or before my first byte
+            if (before == 0) {
+                d0 = w.dead || (nulm & lt) != 0;
+            } else {
+                const uint32_t j = 31u - __clz(before);
+                if (j == lane) d0 = false; // my group starts a packet
+                else if ((bin >> j) & 1u) d0 = ((nafter >> j) & 1u) != 0 || (nulm & lt & ~((2u << j) - 1u)) != 0;
+                else d0 = (nulm & lt & ~((1u << j) - 1u)) != 0;
+            }
+            if ((endm >> lane) & 1u) d0 = true;
+            const bool push_s = cand && !d0 && my_nb >= g + reach;
+            const bool push_c = cand && !push_s && (!d0 || my_nb < g + 16u); // a boundary inside the group can revive it
+            ms = __ballot_sync(FULL, push_s);
+            mc = __ballot_sync(FULL, push_c);
+            // state of the zone the row ends in
+            const uint32_t all = bin | bat;
+            const uint32_t j = 31u - __clz(all); // all != 0: at least one boundary was crossed
+            if (ended) w.dead = true;
+            else if ((bin >> j) & 1u) w.dead = ((nafter >> j) & 1u) != 0 || (nulm & ~((2u << j) - 1u)) != 0;
+            else w.dead = (nulm & ~((1u << j) - 1u)) != 0;
+        }
+
+        // ---- queue flagged groups; drain when a full warp's worth has gathered ----------------------
+        if (ms) {
+            if ((ms >> lane) & 1u) {
+                uint32_t *e = qs + ((w.qs_tail + __popc(ms & lt)) & (UN_QCAP - 1)) * UN_QS_WORDS;
+                *reinterpret_cast<uint4 *>(e) = cur;
+                *reinterpret_cast<uint2 *>(e + 4) = make_uint2(la, w.g16_0 + (g >> 4));
+            }
+            w.qs_tail += __popc(ms);
+            __syncwarp();
+            if (w.qs_tail - w.qs_head >= 32) {
+                verify_simple(p, s_class, s_counts, qs + ((w.qs_head + lane) & (UN_QCAP - 1)) * UN_QS_WORDS, lutlane, mul);
+                w.qs_head += 32;
+                __syncwarp();
+            }
+        }
+        if (mc) {
+            if ((mc >> lane) & 1u) {
+                uint32_t *e = qc + ((w.qc_tail + __popc(mc & lt)) & (UN_QCAP - 1)) * UN_QC_WORDS;
+                *reinterpret_cast<uint4 *>(e) = make_uint4(w.g16_0 + (g >> 4), kz | (d0 ? 0x80000000u : 0u), w.ks, w.ke);
+            }
+            w.qc_tail += __popc(mc);
+            __syncwarp();
+            if (w.qc_tail - w.qc_head >= 32) {
+                const uint4 e = *reinterpret_cast<const uint4 *>(qc + ((w.qc_head + lane) & (UN_QCAP - 1)) * UN_QC_WORDS);
+                w.qc_head += 32;
+                __syncwarp();
+                verify_complex(p, s_class, s_counts, e.x, e.y & 0x7fffffffu, (e.y >> 31) != 0, e.z, e.w);
+            }
+        }
+    };
+
+    auto load_row = [&](uint32_t g) -> uint4 {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (g < w.load_end) v = ld_stream16(w.text + g);
+        return v;
+    };
 
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(&p.work[0], 1u);
         item = __shfl_sync(FULL, item, 0);
         if (item >= p.n_items) break;
-        const uint32_t ks = p.items[item], ke = p.items[item + 1];
-        if (ks >= ke) continue;
-        const uint64_t b_abs = p.offsets[ks], e_abs = p.offsets[ke];
+        w.ks = p.items[item];
+        w.ke = p.items[item + 1];
+        if (w.ks >= w.ke) continue;
+        const uint64_t b_abs = p.offsets[w.ks], e_abs = p.offsets[w.ke];
         if (b_abs == e_abs) continue;
         if (e_abs - b_abs >= (1ull << 31)) { // a packet over 2 GiB: outside the documented limits
             if (lane == 0) atomicOr(&p.work[1], 1u);
             continue;
         }
-        const uint64_t row0 = b_abs & ~127ull;                 // absolute position of the item's first row
-        const uint8_t *text = p.bytes + (row0 - p.abs_base);
-        const uint64_t *off = p.offsets + ks;                  // item boundary j is off[j] - row0
-        const uint32_t nbound = ke - ks;
-        const uint32_t e_rel = (uint32_t)(e_abs - row0);
-        const uint32_t load_end = (e_rel + 15u) & ~15u;
-        const uint32_t g16_0 = (uint32_t)((row0 - p.abs_base) >> 4);
+        w.row0 = b_abs & ~127ull; // absolute position of the item's first row
+        w.text = p.bytes + (w.row0 - p.abs_base);
+        w.off = p.offsets + w.ks;
+        w.nbound = w.ke - w.ks;
+        w.e_rel = (uint32_t)(e_abs - w.row0);
+        w.load_end = (w.e_rel + 15u) & ~15u;
+        w.g16_0 = (uint32_t)((w.row0 - p.abs_base) >> 4);
+        w.zone = 0;
+        w.nb = (uint32_t)(b_abs - w.row0);
+        w.nb_next = (uint32_t)(w.off[1] - w.row0);
+        w.dead = true;
 
-        // zone tracking (warp-uniform): zone 0 = before the first packet (dead), j = packet ks+j-1
-        uint32_t zone = 0;
-        uint32_t nb = (uint32_t)(b_abs - row0);        // boundary that ends the current zone
-        uint32_t nb_next = (uint32_t)(off[1] - row0);  // the one after it (prefetched)
-        bool dead = true;
-
+        // four row buffers rotate roles (scanned / lookahead / two in flight) without register moves:
+        // a row is requested three row-times before it is scanned, two before it serves as lookahead
         uint32_t g = lane * 16u;
-        uint4 cur = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0);
-        if (g < load_end) cur = __ldcs(reinterpret_cast<const uint4 *>(text + g));
-        if (g + UN_ROW < load_end) nx1 = __ldcs(reinterpret_cast<const uint4 *>(text + g + UN_ROW));
-
-        for (uint32_t row = 0; row < e_rel; row += UN_ROW, g += UN_ROW) {
-            uint4 nx2 = make_uint4(0, 0, 0, 0);
-            if (g + 2 * UN_ROW < load_end) nx2 = __ldcs(reinterpret_cast<const uint4 *>(text + g + 2 * UN_ROW));
-            // 3 bytes of lookahead: first word of the next group (next lane, or lane 0 of the next row)
-            const uint32_t la = __shfl_sync(FULL, lane == 0 ? nx1.x : cur.x, (lane + 1) & 31);
-
-            // ---- shift-and filter over 19 bytes --------------------------------------------------
-            uint32_t S, accA, accB, accC;
-            S = LUT_AT(cur.x, 0x5504) & 0x808080ffu; // no history: only the NUL stage is pre-armed
-            accA = S;
-            SA_STEP(cur.x, 0x5514, accA);
-            SA_STEP(cur.x, 0x5524, accA);
-            accB = 0;
-            SA_STEP(cur.x, 0x5534, accB);
-            SA_WORD(cur.y, accB);
-            SA_WORD(cur.z, accB);
-            SA_WORD(cur.w, accB);
-            accC = 0;
-            SA_STEP(la, 0x5504, accC);
-            SA_STEP(la, 0x5514, accC);
-            SA_STEP(la, 0x5524, accC);
-            const bool nul = ((accA | accB) >> 31) != 0;          // a NUL among my 16 bytes
-            const bool cand = ((accB | accC) & 0x7f000000u) != 0; // a candidate start among my 16 positions
-            const uint32_t nulm = __ballot_sync(FULL, nul);
-
-            // ---- which packet am I in, and is it already dead? ----------------------------------
-            const uint32_t row_end = row + UN_ROW;
-            bool push_s = false, push_c = false, d0 = false;
-            uint32_t kz = zone;
-            if (nb >= row_end) { // no packet boundary inside this row
-                d0 = dead || (nulm & lt) != 0;
-                push_s = cand && !d0;
-                if (push_s && nb < g + reach) { push_s = false; push_c = true; } // a boundary within reach
-                dead = dead || nulm != 0;
-            } else {
-                const uint32_t zm = zero_mask16(cur);
-                uint32_t lane_lo = 0;
-                bool seg_dead = dead;
-                for (;;) {
-                    // the current zone covers lanes [lane_lo, lane_hi]: groups that START before nb
-                    const int lane_hi = nb >= row_end ? 31 : ((int)(nb - row) - 1) >> 4;
-                    if ((int)lane >= (int)lane_lo && (int)lane <= lane_hi) {
-                        const uint32_t below = lane_lo >= 32 ? FULL : (1u << lane_lo) - 1u;
-                        kz = zone;
-                        d0 = seg_dead || (nulm & lt & ~below) != 0;
-                        push_s = cand && !d0 && nb >= g + reach;
-                        push_c = cand && !push_s && (!d0 || nb < g + 16u); // a boundary inside the group can revive it
-                    }
-                    if (nb >= row_end) {
-                        const uint32_t below = lane_lo >= 32 ? FULL : (1u << lane_lo) - 1u;
-                        dead = seg_dead || (nulm & ~below) != 0;
-                        break;
-                    }
-                    const uint32_t lb = (nb - row) >> 4, ob = (nb - row) & 15u;
-                    zone++;
-                    if (zone > nbound) { // past the item's last packet
-                        nb = UN_NOBOUND;
-                        seg_dead = true;
-                        lane_lo = lb + (ob ? 1u : 0u);
-                        continue;
-                    }
-                    const uint32_t zlb = __shfl_sync(FULL, zm, lb);
-                    if (ob) { lane_lo = lb + 1u; seg_dead = (zlb >> ob) != 0; }
-                    else { lane_lo = lb; seg_dead = false; }
-                    nb = nb_next;
-                    nb_next = zone + 1 <= nbound ? (uint32_t)(off[zone + 1] - row0) : UN_NOBOUND;
-                }
-            }
-
-            // ---- queue flagged groups; drain when a full warp's worth has gathered -------------
-            const uint32_t ms = __ballot_sync(FULL, push_s);
-            if (ms) {
-                if (push_s) {
-                    uint32_t *e = qs + ((qs_tail + __popc(ms & lt)) & (UN_QCAP - 1)) * UN_QS_WORDS;
-                    *reinterpret_cast<uint4 *>(e) = cur;
-                    *reinterpret_cast<uint2 *>(e + 4) = make_uint2(la, g16_0 + (g >> 4));
-                }
-                qs_tail += __popc(ms);
-                __syncwarp();
-                if (qs_tail - qs_head >= 32) {
-                    verify_simple(p, lut, s_class, s_counts, qs + ((qs_head + lane) & (UN_QCAP - 1)) * UN_QS_WORDS, laneoff);
-                    qs_head += 32;
-                    __syncwarp();
-                }
-            }
-            const uint32_t mc = __ballot_sync(FULL, push_c);
-            if (mc) {
-                if (push_c) {
-                    uint32_t *e = qc + ((qc_tail + __popc(mc & lt)) & (UN_QCAP - 1)) * UN_QC_WORDS;
-                    *reinterpret_cast<uint4 *>(e) = make_uint4(g16_0 + (g >> 4), kz | (d0 ? 0x80000000u : 0u), ks, ke);
-                }
-                qc_tail += __popc(mc);
-                __syncwarp();
-                if (qc_tail - qc_head >= 32) {
-                    const uint4 e = *reinterpret_cast<const uint4 *>(qc + ((qc_head + lane) & (UN_QCAP - 1)) * UN_QC_WORDS);
-                    qc_head += 32;
-                    __syncwarp();
-                    verify_complex(p, s_class, s_counts, e.x, e.y & 0x7fffffffu, (e.y >> 31) != 0, e.z, e.w);
-                }
-            }
-            cur = nx1;
-            nx1 = nx2;
+        uint4 a = load_row(g), b = load_row(g + UN_ROW), c = load_row(g + 2 * UN_ROW), d;
+        for (uint32_t row = 0;;) {
+            d = load_row(g + 3 * UN_ROW);
+            scan_row(a, b, row, g);
+            row += UN_ROW; g += UN_ROW;
+            if (row >= w.e_rel) break;
+            a = load_row(g + 3 * UN_ROW);
+            scan_row(b, c, row, g);
+            row += UN_ROW; g += UN_ROW;
+            if (row >= w.e_rel) break;
+            b = load_row(g + 3 * UN_ROW);
+            scan_row(c, d, row, g);
+            row += UN_ROW; g += UN_ROW;
+            if (row >= w.e_rel) break;
+            c = load_row(g + 3 * UN_ROW);
+            scan_row(d, a, row, g);
+            row += UN_ROW; g += UN_ROW;
+            if (row >= w.e_rel) break;
         }
     }
     // leftovers
     __syncwarp();
-    if (lane < qs_tail - qs_head)
-        verify_simple(p, lut, s_class, s_counts, qs + ((qs_head + lane) & (UN_QCAP - 1)) * UN_QS_WORDS, laneoff);
-    if (lane < qc_tail - qc_head) {
-        const uint4 e = *reinterpret_cast<const uint4 *>(qc + ((qc_head + lane) & (UN_QCAP - 1)) * UN_QC_WORDS);
+    if (lane < w.qs_tail - w.qs_head)
+        verify_simple(p, s_class, s_counts, qs + ((w.qs_head + lane) & (UN_QCAP - 1)) * UN_QS_WORDS, lutlane, mul);
+    if (lane < w.qc_tail - w.qc_head) {
+        const uint4 e = *reinterpret_cast<const uint4 *>(qc + ((w.qc_head + lane) & (UN_QCAP - 1)) * UN_QC_WORDS);
         verify_complex(p, s_class, s_counts, e.x, e.y & 0x7fffffffu, (e.y >> 31) != 0, e.z, e.w);
     }
 
@@ -414,11 +520,10 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     uint32_t *d_items = ctx->d_items + (size_t)slot * ctx->items_cap;
     uint32_t *d_work = ctx->d_work + slot * 4;
 
-    const bool counts_in_smem = h.n_uniq <= KMPB_SMEM_COUNTS_MAX;
-    const size_t smem = UN_SMEM_FIXED + (counts_in_smem ? (size_t)h.n_uniq * sizeof(uint32_t) : 0);
+    const bool counts_in_smem = h.n_uniq <= UN_SMEM_COUNTS_MAX;
+    const size_t smem = UN_SMEM_BYTES;
     if (!ctx->attr_union_set) {
-        KMPB_CUDA(cudaFuncSetAttribute(kmpb_union_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(UN_SMEM_FIXED + KMPB_SMEM_COUNTS_MAX * 4)));
+        KMPB_CUDA(cudaFuncSetAttribute(kmpb_union_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UN_SMEM_BYTES));
         ctx->attr_union_set = true;
     }
     kmpb_union_partition_kernel<<<(n_items + 1 + 255) / 256, 256, 0, stream>>>(b.d_offsets, (uint32_t)b.n_packets, n_items,
@@ -443,6 +548,7 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     p.n_uniq = h.n_uniq;
     p.max_len = h.max_len;
     p.counts_in_smem = counts_in_smem ? 1u : 0u;
+    p.mul256 = 256u;
     p.uniq_counts = (unsigned long long *)d_uniq_counts;
     const uint32_t warps_needed = n_items;
     int grid = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, (warps_needed + UN_WARPS - 1) / UN_WARPS);
