@@ -250,7 +250,8 @@ def ours(args, kmp, patterns):
 
     per_gpu = args.packets
     total_packets = per_gpu * world                      # weak scaling: the stream grows with N
-    first, count = kmp.shard_range(total_packets, world, rank)   # mpi_dumping.c:149-157
+    from multithreading_string_matching_b200 import distributed as kd
+    first, count = kd.rank_slice(total_packets, rank, world)   # mpi_dumping.c:149-157
     L = args.payload_len
     n_pat = len(patterns)
     m = kmp.Matcher(local, engine=args.engine)
@@ -270,7 +271,7 @@ def ours(args, kmp, patterns):
         m.count_device(d_bytes.data_ptr(), d_off.data_ptr(), count, d_counts.data_ptr(), span=(0, nbytes),
                        stream=stream.cuda_stream)
         if world > 1:
-            dist.all_reduce(d_counts)  # the MPI_Reduce(SUM) of mpi_dumping.c:202, over NVLink
+            kd.reduce_counts(d_counts)  # the MPI_Reduce(SUM) of mpi_dumping.c:202, as an NCCL all-reduce over NVLink
 
     def barrier():
         if world > 1:

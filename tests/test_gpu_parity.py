@@ -271,3 +271,25 @@ def test_pattern_sweep_shapes(matchers, oracle):
     # the per-pattern engine tiles pattern sets whose DFAs exceed shared memory
     pats = [bytes(rng.choice(alpha) for _ in range(64)) for _ in range(40)] + [text_pk[0][5:69]]
     check_all(matchers, oracle, pats, text_pk[:40], engines=["perpat"], label="tiled")
+
+
+def test_sharded_slices_add_up(matchers, oracle, strings):
+    """The mpi_dumping.c split on one GPU: each 'rank' matches its own slice of the stream (generated
+    independently from the packet counter), the per-rank vectors sum to the whole-stream counts."""
+    from multithreading_string_matching_b200 import distributed as kd
+
+    total = 20_001
+    synth = kmp.Synth(seed=0xB200, payload_len=1400, plants=2, plant_patterns=strings)
+    m = matchers["union"]
+    m.set_patterns(strings)
+    data, off = synth.fill_host(0, total)
+    want = oracle.count_csr(data, off, strings)
+    for world in (1, 2, 3, 8):
+        acc = [0] * len(strings)
+        covered = 0
+        for rank in range(world):
+            first, count = kd.rank_slice(total, rank, world)
+            sd, so = synth.fill_host(first, count)
+            acc = [a + b for a, b in zip(acc, m.count_host(sd, so))]
+            covered += count
+        assert covered == total and acc == want, world
