@@ -103,7 +103,7 @@ int kmpb_get_prefix(kmpb_ctx *ctx, uint32_t pattern_index, int32_t *pi_out, uint
 int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets, uint64_t n_packets,
                     uint64_t *counts_out);
 
-/* Device form: d_bytes (16-byte aligned, readable up to total_bytes rounded up to 16) and d_offsets
+/* Device form: d_bytes (32-byte aligned, readable up to total_bytes rounded up to 32) and d_offsets
  * are device memory on the context's GPU; d_counts[n_pat] (device, uint64) is ACCUMULATED into, so
  * a caller can sum several batches and all-reduce once (mpi_dumping.c:202).  Asynchronous on
  * `stream` (a cudaStream_t passed as void*; NULL = CUDA's default stream, as in the runtime API).

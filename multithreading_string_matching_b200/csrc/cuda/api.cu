@@ -312,7 +312,9 @@ int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets
         uint32_t work[KMPB_COPY_STREAMS * 4];
         KMPB_CUDA(cudaMemcpy(work, ctx->d_work, sizeof work, cudaMemcpyDeviceToHost));
         for (int s = 0; s < n_slots; s++)
-            if (work[s * 4 + 1]) return kmpb_fail(KMPB_ELIMIT, "a packet of 2 GiB or more is not supported");
+            if (work[s * 4 + 1])
+                return kmpb_fail(KMPB_ELIMIT, work[s * 4 + 1] & 2u ? "unexpected shared-memory window layout on this device"
+                                                                   : "a packet of 2 GiB or more is not supported");
     }
     return KMPB_OK;
 }

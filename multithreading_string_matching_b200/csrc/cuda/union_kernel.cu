@@ -2,10 +2,10 @@
 //
 // Two levels.
 //
-//  FAST PATH (every byte).  A warp streams work items -- runs of whole packets, ~32 KB of the flat
-//  CSR byte buffer -- in rows of 512 contiguous bytes: one coalesced 16-byte load per lane, two rows
-//  in flight ahead of the one being scanned.  Each lane pushes its 16 bytes (+3 bytes of lookahead
-//  from its neighbour, by shuffle) through a 4-byte-deep shift-and filter over 8 buckets:
+//  FAST PATH (every byte).  A warp streams work items -- runs of whole packets, ~64 KB of the flat
+//  CSR byte buffer -- in rows of 1024 contiguous bytes: one coalesced 32-byte load (LDG.256) per lane,
+//  two rows in flight ahead of the one being scanned.  Each lane pushes its 32 bytes (+3 bytes of
+//  lookahead from its neighbour, by shuffle) through a 4-byte-deep shift-and filter over 8 buckets:
 //      S = ((S << 8) | 0xff) & filter[byte]
 //  filter[] lives in shared memory in a bank-private layout (byte address = byte*256 + lane*4) at a
 //  64 KB-aligned shared address, so the one lookup per byte never bank-conflicts and its complete
@@ -14,9 +14,9 @@
 //  bytes are the first 4 bytes (or all the bytes) of some pattern of bucket b"; bit 31 says "this
 //  byte is NUL".
 //
-//  SLOW PATH (rare).  Lanes whose 16 start positions raised a flag push their group into a per-warp
+//  SLOW PATH (rare).  Lanes whose 32 start positions raised a flag push their group into a per-warp
 //  shared-memory ring.  When 32 entries have gathered the warp drains them with every lane busy.
-//    - simple entries (no packet boundary within reach, packet not yet NUL-terminated) carry their 20
+//    - simple entries (no packet boundary within reach, packet not yet NUL-terminated) carry their 36
 //      bytes with them: the lane recomputes which start positions fired and walks the pattern trie
 //      from each of them (start-anchored, so a miss dies after a byte or two);
 //    - complex entries (a packet boundary inside the group or within pattern length of it) take the
@@ -39,26 +39,25 @@
 #ifndef KMPB_UN_ITEM_KB
 #define KMPB_UN_ITEM_KB 64
 #endif
-constexpr int UN_THREADS = KMPB_UN_THREADS; // one block per SM; 768 = 24 warps, up to 85 registers per thread
+constexpr int UN_THREADS = KMPB_UN_THREADS; // one block per SM
 constexpr int UN_WARPS = UN_THREADS / 32;
-constexpr uint32_t UN_ROW = 512;             // bytes per warp row
+constexpr uint32_t UN_GRP = 32;                           // bytes per lane per row
+constexpr uint32_t UN_ROW = 32 * UN_GRP;                  // bytes per warp row
 constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item size
-constexpr uint32_t UN_QCAP = 64;             // ring entries per warp and kind
-constexpr uint32_t UN_QS_WORDS = 8;          // simple entry: 16 B group, 4 B lookahead, group index, pad
-constexpr uint32_t UN_QC_WORDS = 4;          // complex entry: group index, zone|dead, first/last packet of the item
+constexpr uint32_t UN_QCAP = 64;                          // ring entries per warp and kind
+constexpr uint32_t UN_QS_WORDS = 12; // simple entry: 32 B group, 4 B lookahead, group index, pad (48 B)
+constexpr uint32_t UN_QC_WORDS = 4;  // complex entry: group index, zone|dead, first/last packet of the item
 constexpr uint32_t UN_LUT_BYTES = 256 * 256; // 256-byte row per byte value; lanes use the first 128 B
 constexpr uint32_t UN_NOBOUND = 0xffffffffu;
 constexpr uint32_t FULL = 0xffffffffu;
 
 // Dynamic shared memory.  The LUT must start at a 64 KB-aligned shared address; the gap in front of it
-// (63 KB when the dynamic window starts at 0x400, the usual case) holds the simple rings, the byte
-// classes and the counters, the complex rings follow the LUT.  If the gap is too small for them they
-// go behind the complex rings instead; 64 KB + LUT + complex rings covers both layouts, and keeps
-// ~70 KB of the SM's 228 KB as L1 for the trie / automaton tables of the slow path.
+// (63 KB when the dynamic window starts at 0x400, the usual case) holds the complex rings, the byte
+// classes and the counters; the simple rings follow the LUT.
 constexpr uint32_t UN_QS_BYTES = UN_WARPS * UN_QCAP * UN_QS_WORDS * 4;
 constexpr uint32_t UN_QC_BYTES = UN_WARPS * UN_QCAP * UN_QC_WORDS * 4;
-constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_QC_BYTES;
-constexpr uint32_t UN_SMEM_COUNTS_MAX = (65536 - UN_QS_BYTES - 256) / 4 - 64; // distinct patterns counted in shared memory
+constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_QS_BYTES;
+constexpr uint32_t UN_SMEM_COUNTS_MAX = (60 * 1024 - UN_QC_BYTES - 256) / 4; // distinct patterns counted in shared memory
 
 struct union_params {
     const uint8_t *bytes; // device pointer to absolute byte abs_base (abs_base % 512 == 0)
@@ -103,13 +102,15 @@ __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets
 }
 
 // ---- helpers -----------------------------------------------------------------------------------
-// streaming 16-byte load: read once, keep it out of L1 (which holds the slow path's tables)
-__device__ __forceinline__ uint4 ld_stream16(const uint8_t *p)
+struct grp { uint32_t w[8]; }; // one lane's 32 bytes of a row
+
+// streaming 32-byte load: read once, keep it out of L1 (which holds the slow path's tables)
+__device__ __forceinline__ void ld_stream32(const uint8_t *p, grp &g)
 {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(g.w[0]), "=r"(g.w[1]), "=r"(g.w[2]), "=r"(g.w[3]), "=r"(g.w[4]), "=r"(g.w[5]),
+                   "=r"(g.w[6]), "=r"(g.w[7])
+                 : "l"(p));
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
 {
@@ -124,11 +125,13 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t w)
     return ~(t | w | 0x7f7f7f7fu);
 }
 __device__ __forceinline__ uint32_t pack4(uint32_t z) { return (((z >> 7) * 0x00204081u) >> 21) & 0xfu; }
-// bit i set when byte i of the 16-byte group is NUL
-__device__ __forceinline__ uint32_t zero_mask16(const uint4 &v)
+// bit i set when byte i of the 32-byte group is NUL
+__device__ __forceinline__ uint32_t zero_mask32(const uint32_t *w)
 {
-    return pack4(zero_bytes(v.x)) | pack4(zero_bytes(v.y)) << 4 | pack4(zero_bytes(v.z)) << 8 |
-           pack4(zero_bytes(v.w)) << 12;
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) m |= pack4(zero_bytes(w[i])) << (4 * i);
+    return m;
 }
 // mask of lanes >= l (l may be 32)
 __device__ __forceinline__ uint32_t lanes_ge(uint32_t l) { return l >= 32 ? 0u : ~((1u << l) - 1u); }
@@ -165,29 +168,37 @@ __device__ __forceinline__ void count_hit(const union_params &p, uint32_t *s_cou
         SA_NEXT(word, sel);                           \
         cm |= (S & 0x7f000000u) ? (1u << (bit)) : 0u; \
     } while (0)
+#define SV_WORD(word, bit0)              \
+    do {                                 \
+        SV_STEP(word, SEL0, (bit0));     \
+        SV_STEP(word, SEL1, (bit0) + 1); \
+        SV_STEP(word, SEL2, (bit0) + 2); \
+        SV_STEP(word, SEL3, (bit0) + 3); \
+    } while (0)
 
-// Slow path, simple entry: the group's 16 bytes + 4 bytes of lookahead sit in shared memory at
+// Slow path, simple entry: the group's 32 bytes + 4 bytes of lookahead sit in shared memory at
 // `entry`; no packet boundary lies within reach of a match starting in the group and no NUL precedes
 // the group in its packet.  Start-anchored trie walk from every start position that fired.
 __device__ __noinline__ void verify_simple(const union_params &p, const uint8_t *s_class, uint32_t *s_counts,
                                            const uint32_t *entry, uint32_t lutlane, uint32_t mul)
 {
-    const uint4 v = *reinterpret_cast<const uint4 *>(entry);
-    const uint32_t la = entry[4], g16 = entry[5];
+    uint32_t w[8];
+    *reinterpret_cast<uint4 *>(w) = *reinterpret_cast<const uint4 *>(entry);
+    *reinterpret_cast<uint4 *>(w + 4) = *reinterpret_cast<const uint4 *>(entry + 4);
+    const uint32_t la = entry[8], g32 = entry[9];
     uint32_t S, cm = 0;
-    S = LUT_AT(v.x, SEL0) & 0x808080ffu;
-    SA_NEXT(v.x, SEL1);
-    SA_NEXT(v.x, SEL2);
-    SV_STEP(v.x, SEL3, 0);
-    SV_STEP(v.y, SEL0, 1); SV_STEP(v.y, SEL1, 2); SV_STEP(v.y, SEL2, 3); SV_STEP(v.y, SEL3, 4);
-    SV_STEP(v.z, SEL0, 5); SV_STEP(v.z, SEL1, 6); SV_STEP(v.z, SEL2, 7); SV_STEP(v.z, SEL3, 8);
-    SV_STEP(v.w, SEL0, 9); SV_STEP(v.w, SEL1, 10); SV_STEP(v.w, SEL2, 11); SV_STEP(v.w, SEL3, 12);
-    SV_STEP(la, SEL0, 13); SV_STEP(la, SEL1, 14); SV_STEP(la, SEL2, 15);
+    S = LUT_AT(w[0], SEL0) & 0x808080ffu;
+    SA_NEXT(w[0], SEL1);
+    SA_NEXT(w[0], SEL2);
+    SV_STEP(w[0], SEL3, 0);
+    SV_WORD(w[1], 1); SV_WORD(w[2], 5); SV_WORD(w[3], 9); SV_WORD(w[4], 13);
+    SV_WORD(w[5], 17); SV_WORD(w[6], 21); SV_WORD(w[7], 25);
+    SV_STEP(la, SEL0, 29); SV_STEP(la, SEL1, 30); SV_STEP(la, SEL2, 31);
     // starts at or after the group's first NUL are dead (serial.c:191)
-    const uint32_t zm = zero_mask16(v);
+    const uint32_t zm = zero_mask32(w);
     if (zm) cm &= (1u << (__ffs(zm) - 1)) - 1u;
     const uint8_t *eb = reinterpret_cast<const uint8_t *>(entry);
-    const uint8_t *gb = p.bytes + 16ull * g16;
+    const uint8_t *gb = p.bytes + 32ull * g32;
     const uint32_t *trie = p.trie;
     const uint32_t *term = p.state_term;
     const uint32_t ncls = p.n_class;
@@ -196,7 +207,7 @@ __device__ __noinline__ void verify_simple(const union_params &p, const uint8_t 
         cm &= cm - 1;
         uint32_t node = 0;
         for (uint32_t k = i;; k++) {
-            const uint32_t c = k < 20 ? eb[k] : gb[k];
+            const uint32_t c = k < 36 ? eb[k] : gb[k];
             const uint32_t e = __ldg(trie + node * ncls + s_class[c]);
             if (e == 0) break;
             node = e & 0x7fffffffu;
@@ -205,18 +216,18 @@ __device__ __noinline__ void verify_simple(const union_params &p, const uint8_t 
     }
 }
 
-// Slow path, complex entry: general walk.  g16 = group index (16-byte units from abs_base); the
+// Slow path, complex entry: general walk.  g32 = group index (32-byte units from abs_base); the
 // item holds packets [ks, ke); zones: 0 = before the item's first packet (dead), j = packet ks+j-1,
 // > ke-ks = after the item's last packet (dead).  zone = the zone holding the group's first byte,
 // dead = a NUL precedes it inside that packet.  Counts every pattern occurrence that starts in the
 // group, lies inside one packet of the item and has no NUL before it in that packet.
 __device__ __noinline__ void verify_complex(const union_params &p, const uint8_t *s_class, uint32_t *s_counts,
-                                            uint32_t g16, uint32_t zone, bool dead, uint32_t ks, uint32_t ke)
+                                            uint32_t g32, uint32_t zone, bool dead, uint32_t ks, uint32_t ke)
 {
     const uint64_t *off = p.offsets + ks;
     const uint32_t nbound = ke - ks;
-    const uint64_t g = p.abs_base + 16ull * g16;
-    uint64_t limit = g + 15 + p.max_len; // one past the last byte a match starting at g+15 can touch
+    const uint64_t g = p.abs_base + (uint64_t)UN_GRP * g32;
+    uint64_t limit = g + (UN_GRP - 1) + p.max_len; // one past the last byte a match starting at g+31 can touch
     if (limit > off[nbound]) limit = off[nbound];
     uint64_t nb = zone <= nbound ? off[zone] : ~0ull;
     const uint8_t *text = p.bytes - p.abs_base;
@@ -242,21 +253,21 @@ __device__ __noinline__ void verify_complex(const union_params &p, const uint8_t
             const uint32_t o1 = __ldg(p.out_head + state + 1);
             for (uint32_t o = __ldg(p.out_head + state); o < o1; o++) {
                 const uint32_t u = __ldg(p.out_id + o);
-                if (pos + 1 - __ldg(p.uniq_len + u) < g + 16) // start >= g holds: the walk began at g in the root
+                if (pos + 1 - __ldg(p.uniq_len + u) < g + UN_GRP) // start >= g holds: the walk began at g in the root
                     count_hit(p, s_counts, u);
             }
         }
-        if (pos >= g + 15 && state == 0) break; // no match in flight that started inside the group
+        if (pos >= g + (UN_GRP - 1) && state == 0) break; // no match in flight that started inside the group
     }
 }
 
 // per-warp streaming state
 struct warp_state {
     // item
-    const uint8_t *text;  // byte 0 of the item's first row
-    const uint64_t *off;  // item boundary j is off[j] - row0
+    const uint8_t *text; // byte 0 of the item's first row
+    const uint64_t *off; // item boundary j is off[j] - row0
     uint64_t row0;
-    uint32_t nbound, e_rel, load_end, g16_0, ks, ke;
+    uint32_t nbound, e_rel, load_end, g32_0, ks, ke;
     // zone tracking (warp-uniform): zone = boundaries crossed so far; 0 = before the first packet
     uint32_t zone, nb, nb_next;
     bool dead;
@@ -267,84 +278,107 @@ struct warp_state {
 __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_constant__ union_params p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint32_t s_lut_saddr;
     // the LUT sits at the first 64 KB-aligned shared address inside the dynamic allocation
     const uint32_t dyn_saddr = (uint32_t)__cvta_generic_to_shared(smem);
+    uint32_t dyn_size;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
     const uint32_t lut_off = (0x10000u - (dyn_saddr & 0xffffu)) & 0xffffu;
+    const uint32_t front_bytes = UN_QC_BYTES + 256 + 16 + (p.counts_in_smem ? 4u * p.n_uniq : 0u);
+    if (lut_off < front_bytes || lut_off + UN_LUT_BYTES + UN_QS_BYTES > dyn_size) {
+        // unexpected shared-memory window base: refuse rather than compute something wrong
+        if (threadIdx.x == 0) atomicOr(&p.work[1], 2u);
+        return;
+    }
     uint8_t *lut = smem + lut_off;
-    uint32_t *qc_all = reinterpret_cast<uint32_t *>(lut + UN_LUT_BYTES);
-    const uint32_t front_bytes = UN_QS_BYTES + 256 + (p.counts_in_smem ? 4u * p.n_uniq : 0u);
-    uint8_t *front = lut_off >= front_bytes ? smem : lut + UN_LUT_BYTES + UN_QC_BYTES;
-    uint32_t *qs_all = reinterpret_cast<uint32_t *>(front);
-    uint8_t *s_class = front + UN_QS_BYTES;
-    uint32_t *s_counts = p.counts_in_smem ? reinterpret_cast<uint32_t *>(s_class + 256) : nullptr;
+    uint32_t *qs_all = reinterpret_cast<uint32_t *>(lut + UN_LUT_BYTES);
+    uint32_t *qc_all = reinterpret_cast<uint32_t *>(smem);
+    uint8_t *s_class = smem + UN_QC_BYTES;
+    uint32_t *s_lut_saddr = reinterpret_cast<uint32_t *>(s_class + 256);
+    uint32_t *s_counts = p.counts_in_smem ? s_lut_saddr + 4 : nullptr;
 
     for (uint32_t i = threadIdx.x; i < 256 * 32; i += UN_THREADS)
         reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + (i & 31)] = p.filter[i >> 5];
     for (uint32_t i = threadIdx.x; i < 256; i += UN_THREADS) s_class[i] = p.byte_class[i];
     if (s_counts)
         for (uint32_t i = threadIdx.x; i < p.n_uniq; i += UN_THREADS) s_counts[i] = 0;
-    if (threadIdx.x == 0) s_lut_saddr = dyn_saddr + lut_off;
+    if (threadIdx.x == 0) *s_lut_saddr = dyn_saddr + lut_off;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31;
     // read back through shared memory so that no LUT load can be scheduled above the barrier
-    const uint32_t lutlane = s_lut_saddr + (lane << 2);
+    const uint32_t lutlane = *s_lut_saddr + (lane << 2);
     const uint32_t mul = p.mul256;
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t *qs = qs_all + (threadIdx.x >> 5) * (UN_QCAP * UN_QS_WORDS);
     uint32_t *qc = qc_all + (threadIdx.x >> 5) * (UN_QCAP * UN_QC_WORDS);
-    const uint32_t reach = 15u + p.max_len;
+    const uint32_t reach = (UN_GRP - 1) + p.max_len;
     warp_state w;
     w.qs_head = w.qs_tail = w.qc_head = w.qc_tail = 0;
 
-    // one 512-byte row: `cur` is scanned, `nxt` supplies lane 31's lookahead
-    auto scan_row = [&](const uint4 &cur, const uint4 &nxt, const uint32_t row, const uint32_t g) {
+    // one 1024-byte row: `cur` is scanned, `nxt` supplies lane 31's lookahead
+    auto scan_row = [&](const grp &cur, const grp &nxt, const uint32_t row, const uint32_t g) {
         // 3 bytes of lookahead: first word of the next group (next lane, or lane 0 of the next row)
-        const uint32_t la = __shfl_sync(FULL, lane == 0 ? nxt.x : cur.x, (lane + 1) & 31);
+        const uint32_t la = __shfl_sync(FULL, lane == 0 ? nxt.w[0] : cur.w[0], (lane + 1) & 31);
 
-        // ---- shift-and filter over 19 bytes ------------------------------------------------------
-        uint32_t S, accA, accB, accC;
-        S = LUT_AT(cur.x, SEL0) & 0x808080ffu; // no history: only the NUL stage is pre-armed
-        accA = S;
-        SA_STEP(cur.x, SEL1, accA);
-        SA_STEP(cur.x, SEL2, accA);
-        accB = 0;
-        SA_STEP(cur.x, SEL3, accB);
-        SA_WORD(cur.y, accB);
-        SA_WORD(cur.z, accB);
-        SA_WORD(cur.w, accB);
-        accC = 0;
-        SA_STEP(la, SEL0, accC);
-        SA_STEP(la, SEL1, accC);
-        SA_STEP(la, SEL2, accC);
-        const bool nul = ((accA | accB) >> 31) != 0;          // a NUL among my 16 bytes
-        const bool cand = ((accB | accC) & 0x7f000000u) != 0; // a candidate start among my 16 positions
+        // ---- shift-and filter: two independent 19-byte chains (bytes 0..18 and 16..34) so that the
+        //      dependent IMAD -> LOP3 steps of one chain fill the latency gaps of the other ------------
+        uint32_t accA, accB, accC;
+        {
+            uint32_t S, T, tA, tB, tC;
+            S = LUT_AT(cur.w[0], SEL0) & 0x808080ffu; // no history: only the NUL stage is pre-armed
+            T = LUT_AT(cur.w[4], SEL0) & 0x808080ffu;
+            accA = S; tA = T;
+#define SB_STEP(word, sel, acc) do { T = (T * mul + 255u) & LUT_AT(word, sel); acc |= T; } while (0)
+            SA_STEP(cur.w[0], SEL1, accA); SB_STEP(cur.w[4], SEL1, tA);
+            SA_STEP(cur.w[0], SEL2, accA); SB_STEP(cur.w[4], SEL2, tA);
+            accB = 0; tB = 0;
+            SA_STEP(cur.w[0], SEL3, accB); SB_STEP(cur.w[4], SEL3, tB);
+            SA_STEP(cur.w[1], SEL0, accB); SB_STEP(cur.w[5], SEL0, tB);
+            SA_STEP(cur.w[1], SEL1, accB); SB_STEP(cur.w[5], SEL1, tB);
+            SA_STEP(cur.w[1], SEL2, accB); SB_STEP(cur.w[5], SEL2, tB);
+            SA_STEP(cur.w[1], SEL3, accB); SB_STEP(cur.w[5], SEL3, tB);
+            SA_STEP(cur.w[2], SEL0, accB); SB_STEP(cur.w[6], SEL0, tB);
+            SA_STEP(cur.w[2], SEL1, accB); SB_STEP(cur.w[6], SEL1, tB);
+            SA_STEP(cur.w[2], SEL2, accB); SB_STEP(cur.w[6], SEL2, tB);
+            SA_STEP(cur.w[2], SEL3, accB); SB_STEP(cur.w[6], SEL3, tB);
+            SA_STEP(cur.w[3], SEL0, accB); SB_STEP(cur.w[7], SEL0, tB);
+            SA_STEP(cur.w[3], SEL1, accB); SB_STEP(cur.w[7], SEL1, tB);
+            SA_STEP(cur.w[3], SEL2, accB); SB_STEP(cur.w[7], SEL2, tB);
+            SA_STEP(cur.w[3], SEL3, accB); SB_STEP(cur.w[7], SEL3, tB);
+            accC = 0; tC = 0;
+            SA_STEP(cur.w[4], SEL0, accC); SB_STEP(la, SEL0, tC);
+            SA_STEP(cur.w[4], SEL1, accC); SB_STEP(la, SEL1, tC);
+            SA_STEP(cur.w[4], SEL2, accC); SB_STEP(la, SEL2, tC);
+#undef SB_STEP
+            accA |= tA; accB |= tB; accC |= tC;
+        }
+        const bool nul = ((accA | accB) >> 31) != 0;          // a NUL among my 32 bytes
+        const bool cand = ((accB | accC) & 0x7f000000u) != 0; // a candidate start among my 32 positions
         const uint32_t nulm = __ballot_sync(FULL, nul);
         const uint32_t candm = __ballot_sync(FULL, cand);
 
         // ---- which lanes push, and into which ring ------------------------------------------------
         const uint32_t row_end = row + UN_ROW;
-        uint32_t ms, mc;          // lanes pushing a simple / complex entry
-        uint32_t kz = w.zone;     // zone of my group's first byte
-        bool d0 = false;          // my packet already saw a NUL before my group
-        if (w.nb >= row_end) {    // no packet boundary inside this row: everything is warp-uniform
+        uint32_t ms, mc;      // lanes pushing a simple / complex entry
+        uint32_t kz = w.zone; // zone of my group's first byte
+        bool d0 = false;      // my packet already saw a NUL before my group
+        if (w.nb >= row_end) { // no packet boundary inside this row: everything is warp-uniform
             const uint32_t low = nulm & (0u - nulm);
             const uint32_t deadm = w.dead ? FULL : (nulm ? ~((low << 1) - 1u) : 0u); // lanes above the first NUL lane
             const uint32_t alive = candm & ~deadm;
-            // lanes whose reach (group start + 15 + longest pattern) crosses the next boundary
-            const uint32_t nearm = w.nb == UN_NOBOUND ? 0u : lanes_ge(((w.nb - reach - row) >> 4) + 1u);
+            // lanes whose reach (group start + 31 + longest pattern) crosses the next boundary
+            const uint32_t nearm = w.nb == UN_NOBOUND ? 0u : lanes_ge(((w.nb - reach - row) >> 5) + 1u);
             ms = alive & ~nearm;
             mc = alive & nearm;
             w.dead = w.dead || nulm != 0;
         } else {
-            const uint32_t zm = zero_mask16(cur);
+            const uint32_t zm = zero_mask32(cur.w);
             uint32_t bin = 0, bat = 0; // lanes with a boundary inside their group / exactly at its start
             uint32_t endm = 0;         // lanes past the item's last packet
             uint32_t my_ob = 0, my_nb = UN_NOBOUND;
             bool ended = false;
             while (w.nb < row_end) {
-                const uint32_t lb = (w.nb - row) >> 4, ob = (w.nb - row) & 15u;
+                const uint32_t lb = (w.nb - row) >> 5, ob = (w.nb - row) & (UN_GRP - 1);
                 if (w.nb <= g) kz++;
                 else if (my_nb == UN_NOBOUND) my_nb = w.nb;
                 if (ob) {
@@ -377,7 +411,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             }
             if ((endm >> lane) & 1u) d0 = true;
             const bool push_s = cand && !d0 && my_nb >= g + reach;
-            const bool push_c = cand && !push_s && (!d0 || my_nb < g + 16u); // a boundary inside the group can revive it
+            const bool push_c = cand && !push_s && (!d0 || my_nb < g + UN_GRP); // a boundary inside the group can revive it
             ms = __ballot_sync(FULL, push_s);
             mc = __ballot_sync(FULL, push_c);
             // state of the zone the row ends in
@@ -392,8 +426,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         if (ms) {
             if ((ms >> lane) & 1u) {
                 uint32_t *e = qs + ((w.qs_tail + __popc(ms & lt)) & (UN_QCAP - 1)) * UN_QS_WORDS;
-                *reinterpret_cast<uint4 *>(e) = cur;
-                *reinterpret_cast<uint2 *>(e + 4) = make_uint2(la, w.g16_0 + (g >> 4));
+                *reinterpret_cast<uint4 *>(e) = make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]);
+                *reinterpret_cast<uint4 *>(e + 4) = make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]);
+                *reinterpret_cast<uint2 *>(e + 8) = make_uint2(la, w.g32_0 + (g >> 5));
             }
             w.qs_tail += __popc(ms);
             __syncwarp();
@@ -406,7 +441,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         if (mc) {
             if ((mc >> lane) & 1u) {
                 uint32_t *e = qc + ((w.qc_tail + __popc(mc & lt)) & (UN_QCAP - 1)) * UN_QC_WORDS;
-                *reinterpret_cast<uint4 *>(e) = make_uint4(w.g16_0 + (g >> 4), kz | (d0 ? 0x80000000u : 0u), w.ks, w.ke);
+                *reinterpret_cast<uint4 *>(e) = make_uint4(w.g32_0 + (g >> 5), kz | (d0 ? 0x80000000u : 0u), w.ks, w.ke);
             }
             w.qc_tail += __popc(mc);
             __syncwarp();
@@ -419,10 +454,13 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         }
     };
 
-    auto load_row = [&](uint32_t g) -> uint4 {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (g < w.load_end) v = ld_stream16(w.text + g);
-        return v;
+    auto load_row = [&](grp &v, uint32_t g) {
+        if (g < w.load_end) {
+            ld_stream32(w.text + g, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v.w[i] = 0;
+        }
     };
 
     for (;;) {
@@ -444,32 +482,30 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         w.off = p.offsets + w.ks;
         w.nbound = w.ke - w.ks;
         w.e_rel = (uint32_t)(e_abs - w.row0);
-        w.load_end = (w.e_rel + 15u) & ~15u;
-        w.g16_0 = (uint32_t)((w.row0 - p.abs_base) >> 4);
+        w.load_end = (w.e_rel + (UN_GRP - 1)) & ~(UN_GRP - 1);
+        w.g32_0 = (uint32_t)((w.row0 - p.abs_base) >> 5);
         w.zone = 0;
         w.nb = (uint32_t)(b_abs - w.row0);
         w.nb_next = (uint32_t)(w.off[1] - w.row0);
         w.dead = true;
 
-        // four row buffers rotate roles (scanned / lookahead / two in flight) without register moves:
-        // a row is requested three row-times before it is scanned, two before it serves as lookahead
-        uint32_t g = lane * 16u;
-        uint4 a = load_row(g), b = load_row(g + UN_ROW), c = load_row(g + 2 * UN_ROW), d;
+        // three row buffers rotate roles (scanned / lookahead / in flight) without register moves:
+        // a row is requested two row-times before it is scanned, one before it serves as lookahead
+        uint32_t g = lane * UN_GRP;
+        grp a, b, c;
+        load_row(a, g);
+        load_row(b, g + UN_ROW);
         for (uint32_t row = 0;;) {
-            d = load_row(g + 3 * UN_ROW);
+            load_row(c, g + 2 * UN_ROW);
             scan_row(a, b, row, g);
             row += UN_ROW; g += UN_ROW;
             if (row >= w.e_rel) break;
-            a = load_row(g + 3 * UN_ROW);
+            load_row(a, g + 2 * UN_ROW);
             scan_row(b, c, row, g);
             row += UN_ROW; g += UN_ROW;
             if (row >= w.e_rel) break;
-            b = load_row(g + 3 * UN_ROW);
-            scan_row(c, d, row, g);
-            row += UN_ROW; g += UN_ROW;
-            if (row >= w.e_rel) break;
-            c = load_row(g + 3 * UN_ROW);
-            scan_row(d, a, row, g);
+            load_row(b, g + 2 * UN_ROW);
+            scan_row(c, a, row, g);
             row += UN_ROW; g += UN_ROW;
             if (row >= w.e_rel) break;
         }
@@ -510,8 +546,8 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     const kmpb_tables &h = ctx->host;
     if (h.n_uniq == 0 || b.n_packets == 0 || b.end_byte == b.first_byte) return KMPB_OK;
     if (b.n_packets >= (1ull << 31)) return kmpb_fail(KMPB_ELIMIT, "more than 2^31-1 packets in one batch");
-    if ((b.abs_base & 511) || ((uintptr_t)b.d_bytes & 15))
-        return kmpb_fail(KMPB_EINVAL, "payload buffer must be 16-byte aligned");
+    if ((b.abs_base & 511) || ((uintptr_t)b.d_bytes & 31))
+        return kmpb_fail(KMPB_EINVAL, "payload buffer must be 32-byte aligned");
     if (b.end_byte - b.abs_base >= (1ull << 36))
         return kmpb_fail(KMPB_ELIMIT, "more than 64 GiB of payload in one batch");
     const uint64_t span = b.end_byte - b.first_byte;
