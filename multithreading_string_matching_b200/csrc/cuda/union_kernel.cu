@@ -14,11 +14,13 @@
 //  bytes are the first 4 bytes (or all the bytes) of some pattern of bucket b"; bit 31 says "this
 //  byte is NUL".
 //
-//  SLOW PATH (rare).  Lanes whose 32 start positions raised a flag push their group into a per-warp
-//  shared-memory ring.  When 32 entries have gathered the warp drains them with every lane busy.
+//  SLOW PATH (rare).  Lanes whose 32 start positions raised a flag append their group to a per-warp
+//  shared-memory list.  When the list cannot take the next row's entries the warp drains it with
+//  (nearly) every lane busy.
 //    - simple entries (no packet boundary within reach, packet not yet NUL-terminated) carry their 36
 //      bytes with them: the lane recomputes which start positions fired and walks the pattern trie
-//      from each of them (start-anchored, so a miss dies after a byte or two);
+//      (a 16-bit copy in shared memory when it fits) from each of them, start-anchored, so a miss
+//      dies after a byte or two;
 //    - complex entries (a packet boundary inside the group or within pattern length of it) take the
 //      general walk of the union automaton (the merged KMP DFAs, csrc/host/automaton.c), which
 //      follows the offsets array and the reference's "text ends at the first NUL" rule (serial.c:191).
@@ -34,7 +36,7 @@
 #include "kmpb_device.cuh"
 
 #ifndef KMPB_UN_THREADS
-#define KMPB_UN_THREADS 768
+#define KMPB_UN_THREADS 640
 #endif
 #ifndef KMPB_UN_ITEM_KB
 #define KMPB_UN_ITEM_KB 64
@@ -44,20 +46,22 @@ constexpr int UN_WARPS = UN_THREADS / 32;
 constexpr uint32_t UN_GRP = 32;                           // bytes per lane per row
 constexpr uint32_t UN_ROW = 32 * UN_GRP;                  // bytes per warp row
 constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item size
-constexpr uint32_t UN_QCAP = 64;                          // ring entries per warp and kind
-constexpr uint32_t UN_QS_WORDS = 12; // simple entry: 32 B group, 4 B lookahead, group index, pad (48 B)
+constexpr uint32_t UN_QCAP = 32;                          // list entries per warp and kind
+constexpr uint32_t UN_QS_WORDS = 12; // simple entry: 32 B group, 4 B lookahead, group index, NUL flag, pad (48 B)
 constexpr uint32_t UN_QC_WORDS = 4;  // complex entry: group index, zone|dead, first/last packet of the item
 constexpr uint32_t UN_LUT_BYTES = 256 * 256; // 256-byte row per byte value; lanes use the first 128 B
 constexpr uint32_t UN_NOBOUND = 0xffffffffu;
 constexpr uint32_t FULL = 0xffffffffu;
 
 // Dynamic shared memory.  The LUT must start at a 64 KB-aligned shared address; the gap in front of it
-// (63 KB when the dynamic window starts at 0x400, the usual case) holds the complex rings, the byte
-// classes and the counters; the simple rings follow the LUT.
+// (63 KB when the dynamic window starts at 0x400, the usual case) holds the complex lists, per-warp
+// scratch, the byte classes, the counters and the 16-bit trie; the simple lists follow the LUT.
 constexpr uint32_t UN_QS_BYTES = UN_WARPS * UN_QCAP * UN_QS_WORDS * 4;
 constexpr uint32_t UN_QC_BYTES = UN_WARPS * UN_QCAP * UN_QC_WORDS * 4;
+constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 32;
+constexpr uint32_t UN_FRONT_FIXED = UN_QC_BYTES + UN_SCRATCH_BYTES + 256 + 16;
+constexpr uint32_t UN_FRONT_MAX = 60 * 1024; // what the gap is trusted to hold
 constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_QS_BYTES;
-constexpr uint32_t UN_SMEM_COUNTS_MAX = (60 * 1024 - UN_QC_BYTES - 256) / 4; // distinct patterns counted in shared memory
 
 struct union_params {
     const uint8_t *bytes; // device pointer to absolute byte abs_base (abs_base % 512 == 0)
@@ -75,8 +79,9 @@ struct union_params {
     const uint32_t *trie;       // bare trie: child | pattern-ends-here<<31, 0 = no edge
     const uint32_t *state_term; // distinct pattern ending at a state
     const uint8_t *byte_class;
-    uint32_t n_class, n_uniq, max_len;
-    uint32_t counts_in_smem;
+    uint32_t n_class, n_uniq, n_state, max_len;
+    uint32_t counts_in_smem; // counters live in shared memory
+    uint32_t trie_in_smem;   // 16-bit trie + terminal ids live in shared memory
     uint32_t mul256; // the value 256, passed at run time so the shift-or-0xff compiles to an integer
                      // multiply-add on the FMA pipe instead of competing for the ALU pipe
     unsigned long long *uniq_counts;
@@ -112,12 +117,27 @@ __device__ __forceinline__ void ld_stream32(const uint8_t *p, grp &g)
                    "=r"(g.w[6]), "=r"(g.w[7])
                  : "l"(p));
 }
+// loads through 32-bit shared addresses (read-only tables, or data ordered by __syncwarp)
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
 {
     uint32_t v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds8v(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 // 0x80 in every byte of w that is zero (exact, no false positives above a zero byte)
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t w)
 {
@@ -136,9 +156,17 @@ __device__ __forceinline__ uint32_t zero_mask32(const uint32_t *w)
 // mask of lanes >= l (l may be 32)
 __device__ __forceinline__ uint32_t lanes_ge(uint32_t l) { return l >= 32 ? 0u : ~((1u << l) - 1u); }
 
-__device__ __forceinline__ void count_hit(const union_params &p, uint32_t *s_counts, uint32_t u)
+// block-wide shared tables of the slow path
+struct slow_tables {
+    uint32_t class_sa;  // shared address of the 256 byte classes
+    uint32_t trie_sa;   // shared address of the 16-bit trie (trie_in_smem)
+    uint32_t term_sa;   // shared address of the 16-bit terminal ids
+    uint32_t *s_counts; // counters, or nullptr
+};
+
+__device__ __forceinline__ void count_hit(const union_params &p, const slow_tables &t, uint32_t u)
 {
-    if (s_counts) atomicAdd(&s_counts[u], 1u);
+    if (t.s_counts) atomicAdd(&t.s_counts[u], 1u);
     else atomicAdd(p.uniq_counts + u, 1ull);
 }
 
@@ -179,13 +207,13 @@ __device__ __forceinline__ void count_hit(const union_params &p, uint32_t *s_cou
 // Slow path, simple entry: the group's 32 bytes + 4 bytes of lookahead sit in shared memory at
 // `entry`; no packet boundary lies within reach of a match starting in the group and no NUL precedes
 // the group in its packet.  Start-anchored trie walk from every start position that fired.
-__device__ __noinline__ void verify_simple(const union_params &p, const uint8_t *s_class, uint32_t *s_counts,
-                                           const uint32_t *entry, uint32_t lutlane, uint32_t mul)
+__device__ __noinline__ void verify_simple(const union_params &p, const slow_tables &t, const uint32_t *entry,
+                                           uint32_t lutlane, uint32_t mul)
 {
     uint32_t w[8];
     *reinterpret_cast<uint4 *>(w) = *reinterpret_cast<const uint4 *>(entry);
     *reinterpret_cast<uint4 *>(w + 4) = *reinterpret_cast<const uint4 *>(entry + 4);
-    const uint32_t la = entry[8], g32 = entry[9];
+    const uint32_t la = entry[8], g32 = entry[9], has_nul = entry[10];
     uint32_t S, cm = 0;
     S = LUT_AT(w[0], SEL0) & 0x808080ffu;
     SA_NEXT(w[0], SEL1);
@@ -194,24 +222,54 @@ __device__ __noinline__ void verify_simple(const union_params &p, const uint8_t 
     SV_WORD(w[1], 1); SV_WORD(w[2], 5); SV_WORD(w[3], 9); SV_WORD(w[4], 13);
     SV_WORD(w[5], 17); SV_WORD(w[6], 21); SV_WORD(w[7], 25);
     SV_STEP(la, SEL0, 29); SV_STEP(la, SEL1, 30); SV_STEP(la, SEL2, 31);
-    // starts at or after the group's first NUL are dead (serial.c:191)
-    const uint32_t zm = zero_mask32(w);
-    if (zm) cm &= (1u << (__ffs(zm) - 1)) - 1u;
-    const uint8_t *eb = reinterpret_cast<const uint8_t *>(entry);
-    const uint8_t *gb = p.bytes + 32ull * g32;
-    const uint32_t *trie = p.trie;
-    const uint32_t *term = p.state_term;
+    if (has_nul) { // starts at or after the group's first NUL are dead (serial.c:191)
+        const uint32_t zm = zero_mask32(w);
+        if (zm) cm &= (1u << (__ffs(zm) - 1)) - 1u;
+    }
+    const uint32_t entry_sa = saddr_of(entry);
     const uint32_t ncls = p.n_class;
-    while (cm) {
-        const uint32_t i = __ffs(cm) - 1;
-        cm &= cm - 1;
-        uint32_t node = 0;
-        for (uint32_t k = i;; k++) {
-            const uint32_t c = k < 36 ? eb[k] : gb[k];
-            const uint32_t e = __ldg(trie + node * ncls + s_class[c]);
-            if (e == 0) break;
-            node = e & 0x7fffffffu;
-            if (e >> 31) count_hit(p, s_counts, __ldg(term + node));
+    if (p.trie_in_smem) {
+        const uint32_t ncls2 = ncls * 2u;
+        while (cm) {
+            const uint32_t i = __ffs(cm) - 1;
+            cm &= cm - 1;
+            uint32_t row_sa = t.trie_sa; // shared address of the current node's row
+            uint32_t k = i;
+            for (; k < 36; k++) {
+                const uint32_t cls = lds8v(t.class_sa + lds8v(entry_sa + k));
+                const uint32_t e = lds16(row_sa + cls * 2u);
+                if (e == 0) break;
+                const uint32_t node = e & 0x7fffu;
+                row_sa = t.trie_sa + node * ncls2;
+                if (e >> 15) count_hit(p, t, lds16(t.term_sa + node * 2u));
+            }
+            if (k == 36) { // a pattern longer than the bytes carried along: continue in global memory
+                const uint8_t *gb = p.bytes + 32ull * g32;
+                for (;; k++) {
+                    const uint32_t cls = lds8v(t.class_sa + gb[k]);
+                    const uint32_t e = lds16(row_sa + cls * 2u);
+                    if (e == 0) break;
+                    const uint32_t node = e & 0x7fffu;
+                    row_sa = t.trie_sa + node * ncls2;
+                    if (e >> 15) count_hit(p, t, lds16(t.term_sa + node * 2u));
+                }
+            }
+        }
+    } else {
+        const uint8_t *gb = p.bytes + 32ull * g32;
+        const uint32_t *trie = p.trie;
+        const uint32_t *term = p.state_term;
+        while (cm) {
+            const uint32_t i = __ffs(cm) - 1;
+            cm &= cm - 1;
+            uint32_t node = 0;
+            for (uint32_t k = i;; k++) {
+                const uint32_t c = k < 36 ? lds8v(entry_sa + k) : (uint32_t)gb[k];
+                const uint32_t e = __ldg(trie + node * ncls + lds8v(t.class_sa + c));
+                if (e == 0) break;
+                node = e & 0x7fffffffu;
+                if (e >> 31) count_hit(p, t, __ldg(term + node));
+            }
         }
     }
 }
@@ -221,8 +279,8 @@ __device__ __noinline__ void verify_simple(const union_params &p, const uint8_t 
 // > ke-ks = after the item's last packet (dead).  zone = the zone holding the group's first byte,
 // dead = a NUL precedes it inside that packet.  Counts every pattern occurrence that starts in the
 // group, lies inside one packet of the item and has no NUL before it in that packet.
-__device__ __noinline__ void verify_complex(const union_params &p, const uint8_t *s_class, uint32_t *s_counts,
-                                            uint32_t g32, uint32_t zone, bool dead, uint32_t ks, uint32_t ke)
+__device__ __noinline__ void verify_complex(const union_params &p, const slow_tables &t, uint32_t g32, uint32_t zone,
+                                            bool dead, uint32_t ks, uint32_t ke)
 {
     const uint64_t *off = p.offsets + ks;
     const uint32_t nbound = ke - ks;
@@ -247,14 +305,14 @@ __device__ __noinline__ void verify_complex(const union_params &p, const uint8_t
             state = 0;
             continue;
         }
-        const uint32_t e = __ldg(p.next + state * p.n_class + s_class[c]);
+        const uint32_t e = __ldg(p.next + state * p.n_class + lds8v(t.class_sa + c));
         state = e & 0x7fffffffu;
         if (e >> 31) {
             const uint32_t o1 = __ldg(p.out_head + state + 1);
             for (uint32_t o = __ldg(p.out_head + state); o < o1; o++) {
                 const uint32_t u = __ldg(p.out_id + o);
                 if (pos + 1 - __ldg(p.uniq_len + u) < g + UN_GRP) // start >= g holds: the walk began at g in the root
-                    count_hit(p, s_counts, u);
+                    count_hit(p, t, u);
             }
         }
         if (pos >= g + (UN_GRP - 1) && state == 0) break; // no match in flight that started inside the group
@@ -271,19 +329,22 @@ struct warp_state {
     // zone tracking (warp-uniform): zone = boundaries crossed so far; 0 = before the first packet
     uint32_t zone, nb, nb_next;
     bool dead;
-    // rings
-    uint32_t qs_head, qs_tail, qc_head, qc_tail;
+    // pending entries
+    uint32_t qs_n, qc_n;
 };
 
 __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_constant__ union_params p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     // the LUT sits at the first 64 KB-aligned shared address inside the dynamic allocation
-    const uint32_t dyn_saddr = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t dyn_saddr = saddr_of(smem);
     uint32_t dyn_size;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
     const uint32_t lut_off = (0x10000u - (dyn_saddr & 0xffffu)) & 0xffffu;
-    const uint32_t front_bytes = UN_QC_BYTES + 256 + 16 + (p.counts_in_smem ? 4u * p.n_uniq : 0u);
+    const uint32_t counts_bytes = p.counts_in_smem ? 4u * p.n_uniq : 0u;
+    const uint32_t trie_bytes = p.trie_in_smem ? ((2u * p.n_state * p.n_class + 15u) & ~15u) : 0u;
+    const uint32_t term_bytes = p.trie_in_smem ? 2u * p.n_state : 0u;
+    const uint32_t front_bytes = UN_FRONT_FIXED + counts_bytes + trie_bytes + term_bytes;
     if (lut_off < front_bytes || lut_off + UN_LUT_BYTES + UN_QS_BYTES > dyn_size) {
         // unexpected shared-memory window base: refuse rather than compute something wrong
         if (threadIdx.x == 0) atomicOr(&p.work[1], 2u);
@@ -292,72 +353,93 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     uint8_t *lut = smem + lut_off;
     uint32_t *qs_all = reinterpret_cast<uint32_t *>(lut + UN_LUT_BYTES);
     uint32_t *qc_all = reinterpret_cast<uint32_t *>(smem);
-    uint8_t *s_class = smem + UN_QC_BYTES;
+    uint8_t *scratch_all = smem + UN_QC_BYTES;
+    uint8_t *s_class = scratch_all + UN_SCRATCH_BYTES;
     uint32_t *s_lut_saddr = reinterpret_cast<uint32_t *>(s_class + 256);
-    uint32_t *s_counts = p.counts_in_smem ? s_lut_saddr + 4 : nullptr;
+    uint32_t *s_counts = reinterpret_cast<uint32_t *>(s_lut_saddr + 4);
+    uint16_t *s_trie = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(s_counts) + counts_bytes);
+    uint16_t *s_term = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(s_trie) + trie_bytes);
 
     for (uint32_t i = threadIdx.x; i < 256 * 32; i += UN_THREADS)
         reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + (i & 31)] = p.filter[i >> 5];
     for (uint32_t i = threadIdx.x; i < 256; i += UN_THREADS) s_class[i] = p.byte_class[i];
-    if (s_counts)
+    if (p.counts_in_smem)
         for (uint32_t i = threadIdx.x; i < p.n_uniq; i += UN_THREADS) s_counts[i] = 0;
+    if (p.trie_in_smem) {
+        for (uint32_t i = threadIdx.x; i < p.n_state * p.n_class; i += UN_THREADS) {
+            const uint32_t e = p.trie[i];
+            s_trie[i] = (uint16_t)((e & 0x7fffu) | ((e >> 31) << 15));
+        }
+        for (uint32_t i = threadIdx.x; i < p.n_state; i += UN_THREADS) s_term[i] = (uint16_t)p.state_term[i];
+    }
     if (threadIdx.x == 0) *s_lut_saddr = dyn_saddr + lut_off;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = threadIdx.x >> 5;
     // read back through shared memory so that no LUT load can be scheduled above the barrier
     const uint32_t lutlane = *s_lut_saddr + (lane << 2);
     const uint32_t mul = p.mul256;
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t *qs = qs_all + (threadIdx.x >> 5) * (UN_QCAP * UN_QS_WORDS);
-    uint32_t *qc = qc_all + (threadIdx.x >> 5) * (UN_QCAP * UN_QC_WORDS);
+    uint32_t *qs = qs_all + warp * (UN_QCAP * UN_QS_WORDS);
+    uint32_t *qc = qc_all + warp * (UN_QCAP * UN_QC_WORDS);
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(scratch_all + warp * 32);
+    const uint32_t scratch_sa = saddr_of(scratch);
+    slow_tables st;
+    st.class_sa = saddr_of(s_class);
+    st.trie_sa = saddr_of(s_trie);
+    st.term_sa = saddr_of(s_term);
+    st.s_counts = p.counts_in_smem ? s_counts : nullptr;
     const uint32_t reach = (UN_GRP - 1) + p.max_len;
     warp_state w;
-    w.qs_head = w.qs_tail = w.qc_head = w.qc_tail = 0;
+    w.qs_n = w.qc_n = 0;
+
+    auto drain_simple = [&]() {
+        __syncwarp();
+        if (lane < w.qs_n) verify_simple(p, st, qs + lane * UN_QS_WORDS, lutlane, mul);
+        w.qs_n = 0;
+        __syncwarp();
+    };
+    auto drain_complex = [&]() {
+        __syncwarp();
+        if (lane < w.qc_n) {
+            const uint4 e = *reinterpret_cast<const uint4 *>(qc + lane * UN_QC_WORDS);
+            verify_complex(p, st, e.x, e.y & 0x7fffffffu, (e.y >> 31) != 0, e.z, e.w);
+        }
+        w.qc_n = 0;
+        __syncwarp();
+    };
 
     // one 1024-byte row: `cur` is scanned, `nxt` supplies lane 31's lookahead
     auto scan_row = [&](const grp &cur, const grp &nxt, const uint32_t row, const uint32_t g) {
         // 3 bytes of lookahead: first word of the next group (next lane, or lane 0 of the next row)
         const uint32_t la = __shfl_sync(FULL, lane == 0 ? nxt.w[0] : cur.w[0], (lane + 1) & 31);
 
-        // ---- shift-and filter: two independent 19-byte chains (bytes 0..18 and 16..34) so that the
-        //      dependent IMAD -> LOP3 steps of one chain fill the latency gaps of the other ------------
-        uint32_t accA, accB, accC;
-        {
-            uint32_t S, T, tA, tB, tC;
-            S = LUT_AT(cur.w[0], SEL0) & 0x808080ffu; // no history: only the NUL stage is pre-armed
-            T = LUT_AT(cur.w[4], SEL0) & 0x808080ffu;
-            accA = S; tA = T;
-#define SB_STEP(word, sel, acc) do { T = (T * mul + 255u) & LUT_AT(word, sel); acc |= T; } while (0)
-            SA_STEP(cur.w[0], SEL1, accA); SB_STEP(cur.w[4], SEL1, tA);
-            SA_STEP(cur.w[0], SEL2, accA); SB_STEP(cur.w[4], SEL2, tA);
-            accB = 0; tB = 0;
-            SA_STEP(cur.w[0], SEL3, accB); SB_STEP(cur.w[4], SEL3, tB);
-            SA_STEP(cur.w[1], SEL0, accB); SB_STEP(cur.w[5], SEL0, tB);
-            SA_STEP(cur.w[1], SEL1, accB); SB_STEP(cur.w[5], SEL1, tB);
-            SA_STEP(cur.w[1], SEL2, accB); SB_STEP(cur.w[5], SEL2, tB);
-            SA_STEP(cur.w[1], SEL3, accB); SB_STEP(cur.w[5], SEL3, tB);
-            SA_STEP(cur.w[2], SEL0, accB); SB_STEP(cur.w[6], SEL0, tB);
-            SA_STEP(cur.w[2], SEL1, accB); SB_STEP(cur.w[6], SEL1, tB);
-            SA_STEP(cur.w[2], SEL2, accB); SB_STEP(cur.w[6], SEL2, tB);
-            SA_STEP(cur.w[2], SEL3, accB); SB_STEP(cur.w[6], SEL3, tB);
-            SA_STEP(cur.w[3], SEL0, accB); SB_STEP(cur.w[7], SEL0, tB);
-            SA_STEP(cur.w[3], SEL1, accB); SB_STEP(cur.w[7], SEL1, tB);
-            SA_STEP(cur.w[3], SEL2, accB); SB_STEP(cur.w[7], SEL2, tB);
-            SA_STEP(cur.w[3], SEL3, accB); SB_STEP(cur.w[7], SEL3, tB);
-            accC = 0; tC = 0;
-            SA_STEP(cur.w[4], SEL0, accC); SB_STEP(la, SEL0, tC);
-            SA_STEP(cur.w[4], SEL1, accC); SB_STEP(la, SEL1, tC);
-            SA_STEP(cur.w[4], SEL2, accC); SB_STEP(la, SEL2, tC);
-#undef SB_STEP
-            accA |= tA; accB |= tB; accC |= tC;
-        }
+        // ---- shift-and filter over 35 bytes ------------------------------------------------------
+        uint32_t S, accA, accB, accC;
+        S = LUT_AT(cur.w[0], SEL0) & 0x808080ffu; // no history: only the NUL stage is pre-armed
+        accA = S;
+        SA_STEP(cur.w[0], SEL1, accA);
+        SA_STEP(cur.w[0], SEL2, accA);
+        accB = 0;
+        SA_STEP(cur.w[0], SEL3, accB);
+        SA_WORD(cur.w[1], accB);
+        SA_WORD(cur.w[2], accB);
+        SA_WORD(cur.w[3], accB);
+        SA_WORD(cur.w[4], accB);
+        SA_WORD(cur.w[5], accB);
+        SA_WORD(cur.w[6], accB);
+        SA_WORD(cur.w[7], accB);
+        accC = 0;
+        SA_STEP(la, SEL0, accC);
+        SA_STEP(la, SEL1, accC);
+        SA_STEP(la, SEL2, accC);
         const bool nul = ((accA | accB) >> 31) != 0;          // a NUL among my 32 bytes
         const bool cand = ((accB | accC) & 0x7f000000u) != 0; // a candidate start among my 32 positions
         const uint32_t nulm = __ballot_sync(FULL, nul);
         const uint32_t candm = __ballot_sync(FULL, cand);
 
-        // ---- which lanes push, and into which ring ------------------------------------------------
+        // ---- which lanes push, and into which list ------------------------------------------------
         const uint32_t row_end = row + UN_ROW;
         uint32_t ms, mc;      // lanes pushing a simple / complex entry
         uint32_t kz = w.zone; // zone of my group's first byte
@@ -372,10 +454,10 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             mc = alive & nearm;
             w.dead = w.dead || nulm != 0;
         } else {
-            const uint32_t zm = zero_mask32(cur.w);
             uint32_t bin = 0, bat = 0; // lanes with a boundary inside their group / exactly at its start
             uint32_t endm = 0;         // lanes past the item's last packet
-            uint32_t my_ob = 0, my_nb = UN_NOBOUND;
+            uint32_t nafter = 0;       // lanes whose group has a NUL after its last inner boundary
+            uint32_t my_nb = UN_NOBOUND;
             bool ended = false;
             while (w.nb < row_end) {
                 const uint32_t lb = (w.nb - row) >> 5, ob = (w.nb - row) & (UN_GRP - 1);
@@ -383,7 +465,21 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                 else if (my_nb == UN_NOBOUND) my_nb = w.nb;
                 if (ob) {
                     bin |= 1u << lb;
-                    if (lane == lb) my_ob = ob;
+                    if ((nulm >> lb) & 1u) {
+                        // is one of lane lb's NULs at or after the boundary?  lane lb spreads its 32
+                        // bytes through shared memory, lane j looks at byte j
+                        __syncwarp();
+                        if (lane == lb) {
+                            *reinterpret_cast<uint4 *>(scratch) = make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]);
+                            *reinterpret_cast<uint4 *>(scratch + 4) = make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]);
+                        }
+                        __syncwarp();
+                        const bool z = lds8v(scratch_sa + lane) == 0 && lane >= ob;
+                        if (__ballot_sync(FULL, z)) nafter |= 1u << lb;
+                        else nafter &= ~(1u << lb);
+                    } else {
+                        nafter &= ~(1u << lb);
+                    }
                 } else {
                     bat |= 1u << lb;
                 }
@@ -398,8 +494,6 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                 w.nb_next = w.zone + 1 <= w.nbound ? (uint32_t)(w.off[w.zone + 1] - w.row0) : UN_NOBOUND;
             }
             if (my_nb == UN_NOBOUND) my_nb = w.nb;
-            // lanes whose group has a NUL after its last inner boundary
-            const uint32_t nafter = __ballot_sync(FULL, my_ob != 0 && (zm >> my_ob) != 0);
             const uint32_t before = (bin & lt) | (bat & (lt | (1u << lane))); // boundaries at or before my first byte
             if (before == 0) {
                 d0 = w.dead || (nulm & lt) != 0;
@@ -422,35 +516,26 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             else w.dead = (nulm & ~((1u << j) - 1u)) != 0;
         }
 
-        // ---- queue flagged groups; drain when a full warp's worth has gathered ----------------------
+        // ---- append flagged groups; drain first when the list cannot take them ----------------------
         if (ms) {
+            const uint32_t n = __popc(ms);
+            if (w.qs_n + n > UN_QCAP) drain_simple();
             if ((ms >> lane) & 1u) {
-                uint32_t *e = qs + ((w.qs_tail + __popc(ms & lt)) & (UN_QCAP - 1)) * UN_QS_WORDS;
+                uint32_t *e = qs + (w.qs_n + __popc(ms & lt)) * UN_QS_WORDS;
                 *reinterpret_cast<uint4 *>(e) = make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]);
                 *reinterpret_cast<uint4 *>(e + 4) = make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]);
-                *reinterpret_cast<uint2 *>(e + 8) = make_uint2(la, w.g32_0 + (g >> 5));
+                *reinterpret_cast<uint4 *>(e + 8) = make_uint4(la, w.g32_0 + (g >> 5), nul ? 1u : 0u, 0u);
             }
-            w.qs_tail += __popc(ms);
-            __syncwarp();
-            if (w.qs_tail - w.qs_head >= 32) {
-                verify_simple(p, s_class, s_counts, qs + ((w.qs_head + lane) & (UN_QCAP - 1)) * UN_QS_WORDS, lutlane, mul);
-                w.qs_head += 32;
-                __syncwarp();
-            }
+            w.qs_n += n;
         }
         if (mc) {
+            const uint32_t n = __popc(mc);
+            if (w.qc_n + n > UN_QCAP) drain_complex();
             if ((mc >> lane) & 1u) {
-                uint32_t *e = qc + ((w.qc_tail + __popc(mc & lt)) & (UN_QCAP - 1)) * UN_QC_WORDS;
+                uint32_t *e = qc + (w.qc_n + __popc(mc & lt)) * UN_QC_WORDS;
                 *reinterpret_cast<uint4 *>(e) = make_uint4(w.g32_0 + (g >> 5), kz | (d0 ? 0x80000000u : 0u), w.ks, w.ke);
             }
-            w.qc_tail += __popc(mc);
-            __syncwarp();
-            if (w.qc_tail - w.qc_head >= 32) {
-                const uint4 e = *reinterpret_cast<const uint4 *>(qc + ((w.qc_head + lane) & (UN_QCAP - 1)) * UN_QC_WORDS);
-                w.qc_head += 32;
-                __syncwarp();
-                verify_complex(p, s_class, s_counts, e.x, e.y & 0x7fffffffu, (e.y >> 31) != 0, e.z, e.w);
-            }
+            w.qc_n += n;
         }
     };
 
@@ -511,16 +596,11 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         }
     }
     // leftovers
-    __syncwarp();
-    if (lane < w.qs_tail - w.qs_head)
-        verify_simple(p, s_class, s_counts, qs + ((w.qs_head + lane) & (UN_QCAP - 1)) * UN_QS_WORDS, lutlane, mul);
-    if (lane < w.qc_tail - w.qc_head) {
-        const uint4 e = *reinterpret_cast<const uint4 *>(qc + ((w.qc_head + lane) & (UN_QCAP - 1)) * UN_QC_WORDS);
-        verify_complex(p, s_class, s_counts, e.x, e.y & 0x7fffffffu, (e.y >> 31) != 0, e.z, e.w);
-    }
+    drain_simple();
+    drain_complex();
 
     __syncthreads();
-    if (s_counts)
+    if (p.counts_in_smem)
         for (uint32_t u = threadIdx.x; u < p.n_uniq; u += UN_THREADS)
             if (s_counts[u]) atomicAdd(p.uniq_counts + u, (unsigned long long)s_counts[u]);
 }
@@ -556,8 +636,12 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     uint32_t *d_items = ctx->d_items + (size_t)slot * ctx->items_cap;
     uint32_t *d_work = ctx->d_work + slot * 4;
 
-    const bool counts_in_smem = h.n_uniq <= UN_SMEM_COUNTS_MAX;
-    const size_t smem = UN_SMEM_BYTES;
+    // what fits in the shared-memory gap in front of the LUT: counters first, then the 16-bit trie
+    uint32_t front = UN_FRONT_FIXED;
+    const bool counts_in_smem = front + 4ull * h.n_uniq <= UN_FRONT_MAX;
+    if (counts_in_smem) front += 4u * h.n_uniq;
+    const uint64_t trie_need = ((2ull * h.n_state * h.n_class + 15) & ~15ull) + 2ull * h.n_state;
+    const bool trie_in_smem = h.n_state <= 0x7fff && h.n_uniq <= 0xffff && front + trie_need <= UN_FRONT_MAX;
     if (!ctx->attr_union_set) {
         KMPB_CUDA(cudaFuncSetAttribute(kmpb_union_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UN_SMEM_BYTES));
         ctx->attr_union_set = true;
@@ -582,15 +666,17 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     p.byte_class = ctx->dev.byte_class;
     p.n_class = h.n_class;
     p.n_uniq = h.n_uniq;
+    p.n_state = h.n_state;
     p.max_len = h.max_len;
     p.counts_in_smem = counts_in_smem ? 1u : 0u;
+    p.trie_in_smem = trie_in_smem ? 1u : 0u;
     p.mul256 = 256u;
     p.uniq_counts = (unsigned long long *)d_uniq_counts;
     const uint32_t warps_needed = n_items;
     int grid = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, (warps_needed + UN_WARPS - 1) / UN_WARPS);
     if (grid < 1) grid = 1;
     if (ctx->profile) KMPB_CUDA(cudaEventRecord(ctx->ev_kernel[0], stream));
-    kmpb_union_kernel<<<grid, UN_THREADS, smem, stream>>>(p);
+    kmpb_union_kernel<<<grid, UN_THREADS, UN_SMEM_BYTES, stream>>>(p);
     if (ctx->profile) KMPB_CUDA(cudaEventRecord(ctx->ev_kernel[1], stream));
     ctx->launches += 2;
     KMPB_CUDA(cudaGetLastError());
