@@ -329,6 +329,9 @@ struct warp_state {
     // zone tracking (warp-uniform): zone = boundaries crossed so far; 0 = before the first packet
     uint32_t zone, nb, nb_next;
     bool dead;
+    // boundary window: the item's boundaries (relative to row0) are fetched 32 at a time, one per lane;
+    // bcur holds boundaries [bbase, bbase+32), bnxt the 32 after them (already in flight)
+    uint32_t bcur, bnxt, bbase;
     // pending entries
     uint32_t qs_n, qc_n;
 };
@@ -410,6 +413,22 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         __syncwarp();
     };
 
+    // this lane's share of the 32 boundaries starting at boundary index `first`
+    auto boundary_load = [&](uint32_t first) -> uint32_t {
+        const uint32_t j = first + lane;
+        return j <= w.nbound ? (uint32_t)(w.off[j] - w.row0) : UN_NOBOUND;
+    };
+    // after w.zone++: the boundary after the one that now ends the current zone (index zone+1)
+    auto boundary_after_cross = [&]() -> uint32_t {
+        if (w.zone >= w.bbase + 32) {
+            w.bcur = w.bnxt;
+            w.bbase += 32;
+            w.bnxt = boundary_load(w.bbase + 32);
+        }
+        const uint32_t r = w.zone + 1 - w.bbase; // 1..32
+        return __shfl_sync(FULL, r < 32 ? w.bcur : w.bnxt, r & 31);
+    };
+
     // one 1024-byte row: `cur` is scanned, `nxt` supplies lane 31's lookahead
     auto scan_row = [&](const grp &cur, const grp &nxt, const uint32_t row, const uint32_t g) {
         // 3 bytes of lookahead: first word of the next group (next lane, or lane 0 of the next row)
@@ -444,7 +463,11 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         uint32_t ms, mc;      // lanes pushing a simple / complex entry
         uint32_t kz = w.zone; // zone of my group's first byte
         bool d0 = false;      // my packet already saw a NUL before my group
+#ifdef KMPB_ABLATE_BOUNDARY // measurement only (wrong counts): cost of the boundary path
+        if (w.nb >= row_end || w.nb != 0x12345678u) {
+#else
         if (w.nb >= row_end) { // no packet boundary inside this row: everything is warp-uniform
+#endif
             const uint32_t low = nulm & (0u - nulm);
             const uint32_t deadm = w.dead ? FULL : (nulm ? ~((low << 1) - 1u) : 0u); // lanes above the first NUL lane
             const uint32_t alive = candm & ~deadm;
@@ -453,6 +476,49 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             ms = alive & ~nearm;
             mc = alive & nearm;
             w.dead = w.dead || nulm != 0;
+        } else if (w.nb_next >= row_end && w.zone + 1 <= w.nbound) {
+            // exactly one packet boundary inside this row and a packet follows it (the usual case for
+            // packets longer than a row): warp-uniform mask arithmetic, no loop
+            const uint32_t r = w.nb - row, lb = r >> 5, ob = r & (UN_GRP - 1);
+            const uint32_t lbit = 1u << lb, below = lbit - 1u;
+            // old packet: lanes below lb
+            const uint32_t nul_old = nulm & below;
+            const uint32_t low_old = nul_old & (0u - nul_old);
+            const uint32_t dead_old = w.dead ? FULL : (nul_old ? ~((low_old << 1) - 1u) : 0u);
+            const uint32_t alive_old = candm & below & ~dead_old;
+            const uint32_t near_old = lanes_ge(r >= reach ? ((r - reach) >> 5) + 1u : 0u);
+            ms = alive_old & ~near_old;
+            mc = alive_old & near_old;
+            // new packet: lanes above lb, and lane lb itself when the boundary is exactly at its start
+            const uint32_t newm = ob ? ~(below | lbit) : ~below;
+            bool nafter = false; // the new packet has a NUL inside lane lb's group
+            if (ob) {
+                mc |= candm & lbit; // the group holding the boundary: the general walk sorts it out
+                if (lane == lb) d0 = (dead_old & lbit) != 0;
+                if (nulm & lbit) {
+                    // is one of lane lb's NULs at or after the boundary?  lane lb spreads its 32 bytes
+                    // through shared memory, lane j looks at byte j
+                    __syncwarp();
+                    if (lane == lb) {
+                        *reinterpret_cast<uint4 *>(scratch) = make_uint4(cur.w[0], cur.w[1], cur.w[2], cur.w[3]);
+                        *reinterpret_cast<uint4 *>(scratch + 4) = make_uint4(cur.w[4], cur.w[5], cur.w[6], cur.w[7]);
+                    }
+                    __syncwarp();
+                    nafter = __ballot_sync(FULL, lds8v(scratch_sa + lane) == 0 && lane >= ob) != 0;
+                }
+            }
+            const uint32_t nul_new = nulm & newm;
+            const uint32_t low_new = nul_new & (0u - nul_new);
+            const uint32_t dead_new = nafter ? FULL : (nul_new ? ~((low_new << 1) - 1u) : 0u);
+            const uint32_t alive_new = candm & newm & ~dead_new;
+            const uint32_t near_new = w.nb_next == UN_NOBOUND ? 0u : lanes_ge(((w.nb_next - reach - row) >> 5) + 1u);
+            ms |= alive_new & ~near_new;
+            mc |= alive_new & near_new;
+            if ((newm >> lane) & 1u) kz++;
+            w.dead = nafter || nul_new != 0;
+            w.zone++;
+            w.nb = w.nb_next;
+            w.nb_next = boundary_after_cross();
         } else {
             uint32_t bin = 0, bat = 0; // lanes with a boundary inside their group / exactly at its start
             uint32_t endm = 0;         // lanes past the item's last packet
@@ -491,7 +557,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                     break;
                 }
                 w.nb = w.nb_next;
-                w.nb_next = w.zone + 1 <= w.nbound ? (uint32_t)(w.off[w.zone + 1] - w.row0) : UN_NOBOUND;
+                w.nb_next = boundary_after_cross();
             }
             if (my_nb == UN_NOBOUND) my_nb = w.nb;
             const uint32_t before = (bin & lt) | (bat & (lt | (1u << lane))); // boundaries at or before my first byte
@@ -517,6 +583,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         }
 
         // ---- append flagged groups; drain first when the list cannot take them ----------------------
+#ifdef KMPB_ABLATE_SLOW_PATH // measurement only (wrong counts): how fast is the fast path alone?
+        if (ms == 0x12345678u && mc == 0x9abcdef0u)
+#endif
         if (ms) {
             const uint32_t n = __popc(ms);
             if (w.qs_n + n > UN_QCAP) drain_simple();
@@ -570,8 +639,11 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         w.load_end = (w.e_rel + (UN_GRP - 1)) & ~(UN_GRP - 1);
         w.g32_0 = (uint32_t)((w.row0 - p.abs_base) >> 5);
         w.zone = 0;
+        w.bbase = 0;
+        w.bcur = boundary_load(0);
+        w.bnxt = boundary_load(32);
         w.nb = (uint32_t)(b_abs - w.row0);
-        w.nb_next = (uint32_t)(w.off[1] - w.row0);
+        w.nb_next = __shfl_sync(FULL, w.bcur, 1);
         w.dead = true;
 
         // three row buffers rotate roles (scanned / lookahead / in flight) without register moves:
