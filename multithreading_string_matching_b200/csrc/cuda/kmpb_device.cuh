@@ -32,6 +32,7 @@ struct kmpb_device_tables {
     uint32_t *next = nullptr;       // [n_state*n_class]
     uint32_t *trie = nullptr;       // [n_state*n_class]
     uint32_t *state_term = nullptr; // [n_state]
+    uint32_t *vtab = nullptr;       // [vtab_words] start-anchored verification tables (automaton.c)
     uint32_t *out_head = nullptr;   // [n_state+1]
     uint32_t *out_id = nullptr;
     uint8_t *byte_class = nullptr;  // [256]

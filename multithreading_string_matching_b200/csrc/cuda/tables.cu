@@ -61,7 +61,7 @@ void kmpb_release_tables(kmpb_ctx *ctx)
     kmpb_device_tables &d = ctx->dev;
     cudaFree(d.uniq_blob); cudaFree(d.uniq_off); cudaFree(d.uniq_len); cudaFree(d.pat_to_uniq);
     cudaFree(d.pi); cudaFree(d.perpat_dfa); cudaFree(d.next); cudaFree(d.out_head); cudaFree(d.out_id);
-    cudaFree(d.byte_class); cudaFree(d.filter); cudaFree(d.trie); cudaFree(d.state_term);
+    cudaFree(d.byte_class); cudaFree(d.filter); cudaFree(d.trie); cudaFree(d.state_term); cudaFree(d.vtab);
     d = kmpb_device_tables();
     cudaFree(ctx->d_uniq_counts); ctx->d_uniq_counts = nullptr;
     cudaFree(ctx->d_counts); ctx->d_counts = nullptr;
@@ -85,6 +85,7 @@ int kmpb_upload_tables(kmpb_ctx *ctx)
     if ((rc = upload(&d.next, h.next, (size_t)h.n_state * h.n_class, s))) return rc;
     if ((rc = upload(&d.trie, h.trie, (size_t)h.n_state * h.n_class, s))) return rc;
     if ((rc = upload(&d.state_term, h.state_term, (size_t)h.n_state, s))) return rc;
+    if ((rc = upload(&d.vtab, h.vtab, (size_t)h.vtab_words, s))) return rc;
     if ((rc = upload(&d.out_head, h.out_head, (size_t)h.n_state + 1, s))) return rc;
     if ((rc = upload(&d.out_id, h.out_id, (size_t)h.out_head[h.n_state], s))) return rc;
     if ((rc = upload(&d.byte_class, h.byte_class, 256, s))) return rc;

@@ -81,7 +81,9 @@ struct union_params {
     const uint8_t *byte_class;
     uint32_t n_class, n_uniq, n_state, max_len;
     uint32_t counts_in_smem; // counters live in shared memory
-    uint32_t trie_in_smem;   // 16-bit trie + terminal ids live in shared memory
+    uint32_t vtab_in_smem;   // the hash verification tables live in shared memory
+    const uint32_t *vtab;    // hash verification tables (automaton.c build_verify_tables)
+    uint32_t vtab_words;
     uint32_t mul256; // the value 256, passed at run time so the shift-or-0xff compiles to an integer
                      // multiply-add on the FMA pipe instead of competing for the ALU pipe
     unsigned long long *uniq_counts;
@@ -130,11 +132,23 @@ __device__ __forceinline__ uint32_t lds8v(uint32_t saddr)
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ uint32_t lds16(uint32_t saddr)
+__device__ __forceinline__ uint2 lds64(uint32_t saddr)
+{
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32v(uint32_t saddr)
 {
     uint32_t v;
-    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
+}
+// 4 text bytes starting at byte `pos` of a queue entry (pos + 4 <= 36)
+__device__ __forceinline__ uint32_t entry_window(uint32_t entry_sa, uint32_t pos)
+{
+    const uint32_t a = entry_sa + (pos & ~3u);
+    return __funnelshift_r(lds32v(a), lds32v(a + 4), 8u * (pos & 3u));
 }
 __device__ __forceinline__ uint32_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -159,8 +173,7 @@ __device__ __forceinline__ uint32_t lanes_ge(uint32_t l) { return l >= 32 ? 0u :
 // block-wide shared tables of the slow path
 struct slow_tables {
     uint32_t class_sa;  // shared address of the 256 byte classes
-    uint32_t trie_sa;   // shared address of the 16-bit trie (trie_in_smem)
-    uint32_t term_sa;   // shared address of the 16-bit terminal ids
+    uint32_t vtab_sa;   // shared address of the hash verification tables (vtab_in_smem)
     uint32_t *s_counts; // counters, or nullptr
 };
 
@@ -228,30 +241,46 @@ __device__ __noinline__ void verify_simple(const union_params &p, const slow_tab
     }
     const uint32_t entry_sa = saddr_of(entry);
     const uint32_t ncls = p.n_class;
-    if (p.trie_in_smem) {
-        const uint32_t ncls2 = ncls * 2u;
+    if (p.vtab_in_smem) {
+        // Hash verification (tables of csrc/host/automaton.c build_verify_tables, copied to shared
+        // memory): the first min(len,4) bytes of every pattern are a key in the table of that key
+        // length; a hit is confirmed by comparing the remaining pattern words.  No per-byte walk: two or
+        // three dependent shared-memory reads per candidate instead of one per pattern byte.
+        const uint32_t vt = t.vtab_sa;
+        const uint32_t lens = lds32(vt + 44), rec_sa = vt + 4u * lds32(vt + 36), pat_sa = vt + 4u * lds32(vt + 40);
+        const uint8_t *gb = p.bytes + 32ull * g32;
         while (cm) {
             const uint32_t i = __ffs(cm) - 1;
             cm &= cm - 1;
-            uint32_t row_sa = t.trie_sa; // shared address of the current node's row
-            uint32_t k = i;
-            for (; k < 36; k++) {
-                const uint32_t cls = lds8v(t.class_sa + lds8v(entry_sa + k));
-                const uint32_t e = lds16(row_sa + cls * 2u);
-                if (e == 0) break;
-                const uint32_t node = e & 0x7fffu;
-                row_sa = t.trie_sa + node * ncls2;
-                if (e >> 15) count_hit(p, t, lds16(t.term_sa + node * 2u));
-            }
-            if (k == 36) { // a pattern longer than the bytes carried along: continue in global memory
-                const uint8_t *gb = p.bytes + 32ull * g32;
-                for (;; k++) {
-                    const uint32_t cls = lds8v(t.class_sa + gb[k]);
-                    const uint32_t e = lds16(row_sa + cls * 2u);
-                    if (e == 0) break;
-                    const uint32_t node = e & 0x7fffu;
-                    row_sa = t.trie_sa + node * ncls2;
-                    if (e >> 15) count_hit(p, t, lds16(t.term_sa + node * 2u));
+            const uint32_t x0 = entry_window(entry_sa, i);
+#pragma unroll
+            for (uint32_t L = 1; L <= 4; L++) {
+                if (!((lens >> (L - 1)) & 1u)) continue;
+                const uint32_t key = L == 4 ? x0 : x0 & ((1u << (8 * L)) - 1u);
+                const uint32_t mask = lds32(vt + 16u + 4u * L), tab_sa = vt + 4u * lds32(vt + 4u * L);
+                for (uint32_t slot = ((key * 0x9e3779b1u) >> 12) & mask;; slot = (slot + 1) & mask) {
+                    const uint2 e = lds64(tab_sa + 8u * slot);
+                    if (e.y == 0xffffffffu) break;
+                    if (e.x != key) continue;
+                    for (uint32_t u = e.y; u != 0xffffffffu; u = lds32(rec_sa + 12u * u + 8u)) {
+                        const uint32_t m = lds32(rec_sa + 12u * u), pw_sa = pat_sa + 4u * lds32(rec_sa + 12u * u + 4u);
+                        bool same = true;
+                        for (uint32_t j = 4; j < m && same; j += 4) { // pattern bytes j..j+3 against text bytes i+j..
+                            const uint32_t pw = lds32(pw_sa + j), rem = m - j;
+                            if (i + j + 4 <= 36) {
+                                const uint32_t diff = entry_window(entry_sa, i + j) ^ pw;
+                                same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
+                            } else { // past the bytes carried along: byte by byte, entry first, then global memory
+                                for (uint32_t b = 0; b < 4 && b < rem && same; b++) {
+                                    const uint32_t pos = i + j + b;
+                                    const uint32_t c = pos < 36 ? lds8v(entry_sa + pos) : (uint32_t)gb[pos];
+                                    same = c == ((pw >> (8 * b)) & 0xffu);
+                                }
+                            }
+                        }
+                        if (same) count_hit(p, t, u);
+                    }
+                    break;
                 }
             }
         }
@@ -344,10 +373,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     uint32_t dyn_size;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
     const uint32_t lut_off = (0x10000u - (dyn_saddr & 0xffffu)) & 0xffffu;
-    const uint32_t counts_bytes = p.counts_in_smem ? 4u * p.n_uniq : 0u;
-    const uint32_t trie_bytes = p.trie_in_smem ? ((2u * p.n_state * p.n_class + 15u) & ~15u) : 0u;
-    const uint32_t term_bytes = p.trie_in_smem ? 2u * p.n_state : 0u;
-    const uint32_t front_bytes = UN_FRONT_FIXED + counts_bytes + trie_bytes + term_bytes;
+    const uint32_t counts_bytes = p.counts_in_smem ? ((4u * p.n_uniq + 15u) & ~15u) : 0u;
+    const uint32_t vtab_bytes = p.vtab_in_smem ? 4u * p.vtab_words : 0u;
+    const uint32_t front_bytes = UN_FRONT_FIXED + counts_bytes + vtab_bytes;
     if (lut_off < front_bytes || lut_off + UN_LUT_BYTES + UN_QS_BYTES > dyn_size) {
         // unexpected shared-memory window base: refuse rather than compute something wrong
         if (threadIdx.x == 0) atomicOr(&p.work[1], 2u);
@@ -360,21 +388,15 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     uint8_t *s_class = scratch_all + UN_SCRATCH_BYTES;
     uint32_t *s_lut_saddr = reinterpret_cast<uint32_t *>(s_class + 256);
     uint32_t *s_counts = reinterpret_cast<uint32_t *>(s_lut_saddr + 4);
-    uint16_t *s_trie = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(s_counts) + counts_bytes);
-    uint16_t *s_term = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(s_trie) + trie_bytes);
+    uint32_t *s_vtab = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_counts) + counts_bytes);
 
     for (uint32_t i = threadIdx.x; i < 256 * 32; i += UN_THREADS)
         reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + (i & 31)] = p.filter[i >> 5];
     for (uint32_t i = threadIdx.x; i < 256; i += UN_THREADS) s_class[i] = p.byte_class[i];
     if (p.counts_in_smem)
         for (uint32_t i = threadIdx.x; i < p.n_uniq; i += UN_THREADS) s_counts[i] = 0;
-    if (p.trie_in_smem) {
-        for (uint32_t i = threadIdx.x; i < p.n_state * p.n_class; i += UN_THREADS) {
-            const uint32_t e = p.trie[i];
-            s_trie[i] = (uint16_t)((e & 0x7fffu) | ((e >> 31) << 15));
-        }
-        for (uint32_t i = threadIdx.x; i < p.n_state; i += UN_THREADS) s_term[i] = (uint16_t)p.state_term[i];
-    }
+    if (p.vtab_in_smem)
+        for (uint32_t i = threadIdx.x; i < p.vtab_words; i += UN_THREADS) s_vtab[i] = p.vtab[i];
     if (threadIdx.x == 0) *s_lut_saddr = dyn_saddr + lut_off;
     __syncthreads();
 
@@ -390,8 +412,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     const uint32_t scratch_sa = saddr_of(scratch);
     slow_tables st;
     st.class_sa = saddr_of(s_class);
-    st.trie_sa = saddr_of(s_trie);
-    st.term_sa = saddr_of(s_term);
+    st.vtab_sa = saddr_of(s_vtab);
     st.s_counts = p.counts_in_smem ? s_counts : nullptr;
     const uint32_t reach = (UN_GRP - 1) + p.max_len;
     warp_state w;
@@ -646,25 +667,20 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         w.nb_next = __shfl_sync(FULL, w.bcur, 1);
         w.dead = true;
 
-        // three row buffers rotate roles (scanned / lookahead / in flight) without register moves:
-        // a row is requested two row-times before it is scanned, one before it serves as lookahead
+        // three row buffers (scanned / lookahead / in flight): a row is requested two row-times before
+        // it is scanned, one before it serves as lookahead.  The buffers rotate by register moves (16
+        // IMAD.MOVs on the otherwise idle FMA pipe) rather than by unrolling the row body three times:
+        // the unrolled kernel no longer fits the instruction cache (ncu: stall_no_instruction 3.6/issue).
         uint32_t g = lane * UN_GRP;
         grp a, b, c;
         load_row(a, g);
         load_row(b, g + UN_ROW);
-        for (uint32_t row = 0;;) {
+#pragma unroll 1
+        for (uint32_t row = 0; row < w.e_rel; row += UN_ROW, g += UN_ROW) {
             load_row(c, g + 2 * UN_ROW);
             scan_row(a, b, row, g);
-            row += UN_ROW; g += UN_ROW;
-            if (row >= w.e_rel) break;
-            load_row(a, g + 2 * UN_ROW);
-            scan_row(b, c, row, g);
-            row += UN_ROW; g += UN_ROW;
-            if (row >= w.e_rel) break;
-            load_row(b, g + 2 * UN_ROW);
-            scan_row(c, a, row, g);
-            row += UN_ROW; g += UN_ROW;
-            if (row >= w.e_rel) break;
+            a = b;
+            b = c;
         }
     }
     // leftovers
@@ -710,10 +726,9 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
 
     // what fits in the shared-memory gap in front of the LUT: counters first, then the 16-bit trie
     uint32_t front = UN_FRONT_FIXED;
-    const bool counts_in_smem = front + 4ull * h.n_uniq <= UN_FRONT_MAX;
-    if (counts_in_smem) front += 4u * h.n_uniq;
-    const uint64_t trie_need = ((2ull * h.n_state * h.n_class + 15) & ~15ull) + 2ull * h.n_state;
-    const bool trie_in_smem = h.n_state <= 0x7fff && h.n_uniq <= 0xffff && front + trie_need <= UN_FRONT_MAX;
+    const bool counts_in_smem = front + 4ull * h.n_uniq + 16 <= UN_FRONT_MAX;
+    if (counts_in_smem) front += (4u * h.n_uniq + 15u) & ~15u;
+    const bool vtab_in_smem = front + 4ull * h.vtab_words <= UN_FRONT_MAX;
     if (!ctx->attr_union_set) {
         KMPB_CUDA(cudaFuncSetAttribute(kmpb_union_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UN_SMEM_BYTES));
         ctx->attr_union_set = true;
@@ -741,7 +756,9 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     p.n_state = h.n_state;
     p.max_len = h.max_len;
     p.counts_in_smem = counts_in_smem ? 1u : 0u;
-    p.trie_in_smem = trie_in_smem ? 1u : 0u;
+    p.vtab_in_smem = vtab_in_smem ? 1u : 0u;
+    p.vtab = ctx->dev.vtab;
+    p.vtab_words = h.vtab_words;
     p.mul256 = 256u;
     p.uniq_counts = (unsigned long long *)d_uniq_counts;
     const uint32_t warps_needed = n_items;

@@ -265,6 +265,87 @@ static int build_dfa(kmpb_tables *t)
     return KMPB_OK;
 }
 
+/* ---- start-anchored verification tables ---------------------------------------------------------- */
+
+#define VT_HEADER 12
+#define VT_EMPTY 0xffffffffu
+
+uint32_t kmpb_vtab_hash(uint32_t key, uint32_t mask) { return ((key * 0x9e3779b1u) >> 12) & mask; }
+
+/* first min(len,4) bytes of a pattern as a little-endian word */
+static uint32_t key_of(const uint8_t *p, uint32_t len)
+{
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < 4 && i < len; i++) k |= (uint32_t)p[i] << (8 * i);
+    return k;
+}
+
+static int build_verify_tables(kmpb_tables *t)
+{
+    uint32_t count[5] = {0, 0, 0, 0, 0}, slots[5] = {0, 0, 0, 0, 0}, toff[5] = {0, 0, 0, 0, 0};
+    uint32_t blob_words = 0;
+    for (uint32_t u = 0; u < t->n_uniq; u++) {
+        uint32_t L = t->uniq_len[u] < 4 ? t->uniq_len[u] : 4;
+        count[L]++;
+        blob_words += (t->uniq_len[u] + 3) / 4;
+    }
+    uint32_t at = VT_HEADER;
+    for (uint32_t L = 1; L <= 4; L++) {
+        if (count[L] == 0) continue;
+        uint32_t n = 8;
+        while (n < 2 * count[L]) n *= 2; /* load factor <= 0.5: short probe sequences */
+        if (n > (1u << 20)) return kmpb_fail(KMPB_ELIMIT, "too many patterns for the verification tables");
+        slots[L] = n;
+        toff[L] = at;
+        at += 2 * n;
+    }
+    const uint32_t rec_off = at;
+    at += 3 * t->n_uniq;
+    const uint32_t blob_off = at;
+    at += blob_words;
+    uint32_t *v = calloc(at ? at : 1, sizeof *v);
+    if (!v) return kmpb_fail(KMPB_ENOMEM, "out of memory building the verification tables");
+    v[0] = at;
+    for (uint32_t L = 1; L <= 4; L++) {
+        v[L] = toff[L];
+        v[4 + L] = slots[L] ? slots[L] - 1 : 0;
+        if (slots[L]) v[11] |= 1u << (L - 1);
+        for (uint32_t s = 0; s < slots[L]; s++) v[toff[L] + 2 * s + 1] = VT_EMPTY;
+    }
+    v[9] = rec_off;
+    v[10] = blob_off;
+    uint32_t bw = 0;
+    for (uint32_t u = 0; u < t->n_uniq; u++) {
+        const uint8_t *p = t->uniq_blob + t->uniq_off[u];
+        const uint32_t len = t->uniq_len[u], L = len < 4 ? len : 4, key = key_of(p, len);
+        uint32_t *rec = v + rec_off + 3 * u;
+        rec[0] = len;
+        rec[1] = bw;
+        rec[2] = VT_EMPTY;
+        memcpy((uint8_t *)(v + blob_off + bw), p, len); /* rest of the last word stays zero */
+        bw += (len + 3) / 4;
+        /* insert: same key -> chain (only possible for len >= 4; shorter patterns are distinct keys) */
+        uint32_t s = kmpb_vtab_hash(key, slots[L] - 1);
+        for (;;) {
+            uint32_t *slot = v + toff[L] + 2 * s;
+            if (slot[1] == VT_EMPTY) {
+                slot[0] = key;
+                slot[1] = u;
+                break;
+            }
+            if (slot[0] == key) {
+                rec[2] = slot[1]; /* push front */
+                slot[1] = u;
+                break;
+            }
+            s = (s + 1) & (slots[L] - 1);
+        }
+    }
+    t->vtab = v;
+    t->vtab_words = at;
+    return KMPB_OK;
+}
+
 /* ---- entry points ----------------------------------------------------------------------------- */
 
 int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat)
@@ -325,6 +406,7 @@ int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_o
     free(refs);
 
     int rc = build_dfa(t);
+    if (rc == KMPB_OK) rc = build_verify_tables(t);
     if (rc == KMPB_OK) build_filter(t, uniq);
     free(uniq);
     if (rc != KMPB_OK) kmpb_tables_free(t);
@@ -342,5 +424,6 @@ void kmpb_tables_free(kmpb_tables *t)
     free(t->state_term);
     free(t->out_head);
     free(t->out_id);
+    free(t->vtab);
     memset(t, 0, sizeof *t);
 }

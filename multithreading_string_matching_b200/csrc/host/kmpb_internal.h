@@ -49,9 +49,23 @@ typedef struct kmpb_tables {
      * is the NUL detector, buckets 7 of depths 0..2 are always set */
     uint32_t filter[256];
     uint32_t bucket_of_uniq_valid; /* 1 when filter[] is usable (n_uniq > 0) */
+
+    /* start-anchored verification tables (the device's slow path): one open-addressing hash table per
+     * key length L = 1..4, keyed by the first min(len, 4) bytes of a pattern (little-endian u32).
+     * Layout of vtab (u32 words):
+     *   [0] total words   [1..4] word offset of table L (0 = none)   [5..8] slot mask of table L
+     *   [9] word offset of the records   [10] word offset of the pattern words   [11] bit L-1 set when table L exists
+     *   tables: slots of 2 words {key, first record or 0xffffffff}
+     *   records (3 words per distinct pattern): {length, word offset of its bytes inside the pattern words,
+     *            next record with the same 4-byte key or 0xffffffff}
+     *   pattern words: every pattern zero-padded to a multiple of 4 bytes */
+    uint32_t *vtab;
+    uint32_t vtab_words;
     double filter_fp_estimate;     /* estimated candidate probability per text byte, uniform bytes */
 } kmpb_tables;
 
+/* slot of `key` in a verification table with `mask`+1 slots (the device uses the same expression) */
+uint32_t kmpb_vtab_hash(uint32_t key, uint32_t mask);
 int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat);
 void kmpb_tables_free(kmpb_tables *t);
 

@@ -75,6 +75,33 @@ static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int
     for (uint32_t u = 0; u < t.n_uniq; u++)
         if (got_trie[u] != got[u]) { fprintf(stderr, "uniq %u: trie %llu dfa %llu\n", u, (unsigned long long)got_trie[u], (unsigned long long)got[u]); bad = 1; }
     free(got_trie);
+    /* 1c. the hash verification tables, probed at every start position, report the same counts */
+    if (t.n_uniq) {
+        const uint32_t *v = t.vtab;
+        uint64_t *got_hash = calloc((size_t)t.n_uniq + 1, sizeof *got_hash);
+        for (int s = 0; s < text_len; s++) {
+            uint32_t x0 = 0;
+            for (int k = 0; k < 4; k++) x0 |= (uint32_t)text[s + k] << (8 * k); /* text is zero padded */
+            for (uint32_t L = 1; L <= 4; L++) {
+                if (!((v[11] >> (L - 1)) & 1u)) continue;
+                const uint32_t key = L == 4 ? x0 : x0 & ((1u << (8 * L)) - 1u), mask = v[4 + L];
+                for (uint32_t slot = kmpb_vtab_hash(key, mask);; slot = (slot + 1) & mask) {
+                    const uint32_t *e = v + v[L] + 2 * slot;
+                    if (e[1] == 0xffffffffu) break;
+                    if (e[0] != key) continue;
+                    for (uint32_t u = e[1]; u != 0xffffffffu; u = v[v[9] + 3 * u + 2]) {
+                        const uint32_t len = v[v[9] + 3 * u];
+                        const uint8_t *pb = (const uint8_t *)(v + v[10] + v[v[9] + 3 * u + 1]);
+                        if (s + (int)len <= text_len && memcmp(text + s, pb, len) == 0) got_hash[u]++;
+                    }
+                    break;
+                }
+            }
+        }
+        for (uint32_t u = 0; u < t.n_uniq; u++)
+            if (got_hash[u] != got[u]) { fprintf(stderr, "uniq %u: hash %llu dfa %llu\n", u, (unsigned long long)got_hash[u], (unsigned long long)got[u]); bad = 1; }
+        free(got_hash);
+    }
     for (int p = 0; p < n_pat; p++) {
         int len = (int)(off[p + 1] - off[p]);
         uint64_t want = 0;
