@@ -456,7 +456,41 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         const uint32_t la = __shfl_sync(FULL, lane == 0 ? nxt.w[0] : cur.w[0], (lane + 1) & 31);
 
         // ---- shift-and filter over 35 bytes ------------------------------------------------------
-        uint32_t S, accA, accB, accC;
+        uint32_t accA, accB, accC;
+#ifdef KMPB_UN_TWO_CHAINS
+        // two independent 19-byte chains (bytes 0..18 and 16..34): the dependent IMAD -> LOP3 steps of
+        // one fill the latency gaps of the other, at the price of 3 extra steps
+        {
+            uint32_t S, T, tA, tB, tC;
+            S = LUT_AT(cur.w[0], SEL0) & 0x808080ffu;
+            T = LUT_AT(cur.w[4], SEL0) & 0x808080ffu;
+            accA = S; tA = T;
+#define SB_STEP(word, sel, acc) do { T = (T * mul + 255u) & LUT_AT(word, sel); acc |= T; } while (0)
+            SA_STEP(cur.w[0], SEL1, accA); SB_STEP(cur.w[4], SEL1, tA);
+            SA_STEP(cur.w[0], SEL2, accA); SB_STEP(cur.w[4], SEL2, tA);
+            accB = 0; tB = 0;
+            SA_STEP(cur.w[0], SEL3, accB); SB_STEP(cur.w[4], SEL3, tB);
+            SA_STEP(cur.w[1], SEL0, accB); SB_STEP(cur.w[5], SEL0, tB);
+            SA_STEP(cur.w[1], SEL1, accB); SB_STEP(cur.w[5], SEL1, tB);
+            SA_STEP(cur.w[1], SEL2, accB); SB_STEP(cur.w[5], SEL2, tB);
+            SA_STEP(cur.w[1], SEL3, accB); SB_STEP(cur.w[5], SEL3, tB);
+            SA_STEP(cur.w[2], SEL0, accB); SB_STEP(cur.w[6], SEL0, tB);
+            SA_STEP(cur.w[2], SEL1, accB); SB_STEP(cur.w[6], SEL1, tB);
+            SA_STEP(cur.w[2], SEL2, accB); SB_STEP(cur.w[6], SEL2, tB);
+            SA_STEP(cur.w[2], SEL3, accB); SB_STEP(cur.w[6], SEL3, tB);
+            SA_STEP(cur.w[3], SEL0, accB); SB_STEP(cur.w[7], SEL0, tB);
+            SA_STEP(cur.w[3], SEL1, accB); SB_STEP(cur.w[7], SEL1, tB);
+            SA_STEP(cur.w[3], SEL2, accB); SB_STEP(cur.w[7], SEL2, tB);
+            SA_STEP(cur.w[3], SEL3, accB); SB_STEP(cur.w[7], SEL3, tB);
+            accC = 0; tC = 0;
+            SA_STEP(cur.w[4], SEL0, accC); SB_STEP(la, SEL0, tC);
+            SA_STEP(cur.w[4], SEL1, accC); SB_STEP(la, SEL1, tC);
+            SA_STEP(cur.w[4], SEL2, accC); SB_STEP(la, SEL2, tC);
+#undef SB_STEP
+            accA |= tA; accB |= tB; accC |= tC;
+        }
+#else
+        uint32_t S;
         S = LUT_AT(cur.w[0], SEL0) & 0x808080ffu; // no history: only the NUL stage is pre-armed
         accA = S;
         SA_STEP(cur.w[0], SEL1, accA);
@@ -474,6 +508,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         SA_STEP(la, SEL0, accC);
         SA_STEP(la, SEL1, accC);
         SA_STEP(la, SEL2, accC);
+#endif
         const bool nul = ((accA | accB) >> 31) != 0;          // a NUL among my 32 bytes
         const bool cand = ((accB | accC) & 0x7f000000u) != 0; // a candidate start among my 32 positions
         const uint32_t nulm = __ballot_sync(FULL, nul);
