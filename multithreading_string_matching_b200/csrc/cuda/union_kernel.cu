@@ -65,7 +65,8 @@ constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_WORDS * 4;
 constexpr uint32_t UN_RING_BYTES = UN_WARPS * UN_SLOTS * UN_SLOT_BYTES;
 constexpr uint32_t UN_MBAR_BYTES = UN_WARPS * 8 * UN_SLOTS;
-constexpr uint32_t UN_FRONT_FIXED = UN_Q_BYTES + 16;
+constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
+constexpr uint32_t UN_FRONT_FIXED = UN_Q_BYTES + UN_SCRATCH_BYTES + 16;
 constexpr uint32_t UN_FRONT_MAX = 60 * 1024; // what the gap is trusted to hold
 constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_RING_BYTES + UN_MBAR_BYTES;
 static_assert(UN_FRONT_FIXED + 1024 <= UN_FRONT_MAX, "event lists do not fit in front of the LUT");
@@ -203,20 +204,11 @@ __device__ __forceinline__ uint32_t bit_window(uint32_t lo, uint32_t hi)
 #define SEL2 0x7624
 #define SEL3 0x7634
 #define SA_NEXT(word, sel) (S = (S * mul + 255u) & LUT_AT(word, sel))
-#ifdef KMPB_UN_SUM_ACC
-// accumulate the top bytes as a sum on the FMA pipe (IMAD.HI): nonzero iff some step raised a flag
-#define SA_STEP(word, sel, acc)       \
-    do {                              \
-        SA_NEXT(word, sel);           \
-        acc = __umulhi(S, mul) + acc; \
-    } while (0)
-#else
 #define SA_STEP(word, sel, acc) \
     do {                        \
         SA_NEXT(word, sel);     \
         acc |= S;               \
     } while (0)
-#endif
 #define SA_WORD(word, acc)        \
     do {                          \
         SA_STEP(word, SEL0, acc); \
@@ -248,7 +240,8 @@ struct slow_ctx {
     const uint32_t *vtab_g; // verification tables in global memory
     uint32_t vtab_sa;       // ... or their shared address (vtab_in_smem)
     uint32_t vtab_in_smem;
-    uint32_t *s_counts; // shared counters, or nullptr
+    uint32_t scratch_sa;    // 32 words of per-warp scratch
+    uint32_t *s_counts;     // shared counters, or nullptr
     unsigned long long *g_counts;
 };
 
@@ -261,12 +254,15 @@ __device__ __forceinline__ void count_hit(const slow_ctx &c, uint32_t u)
 // Every pattern that starts at byte `i` of the event at entry_sa (whose group starts at absolute byte
 // gq) and is at most `room` bytes long is counted.
 template <bool VS>
-__device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_sa, uint32_t i, uint64_t gq, uint32_t room)
+__device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_sa, uint32_t i, uint32_t room)
 {
     auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(c.vtab_sa + 4u * word) : __ldg(c.vtab_g + word); };
-    const uint32_t lens = vt(11), rec0 = vt(9), pat0 = vt(10);
-    const uint8_t *gb = c.bytes + (gq - c.abs_base);
     const uint32_t x0 = entry_window(entry_sa, i);
+    // key lengths of the patterns that start with this byte
+    const uint32_t b0 = x0 & 0xffu;
+    const uint32_t lens = VS ? lds8v(c.vtab_sa + 48u + b0) : (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(c.vtab_g + 12) + b0);
+    if (lens == 0) return;
+    const uint32_t rec0 = vt(9), pat0 = vt(10);
 #pragma unroll
     for (uint32_t L = 1; L <= 4; L++) {
         if (!((lens >> (L - 1)) & 1u) || L > room) continue;
@@ -286,6 +282,7 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_s
                         const uint32_t diff = entry_window(entry_sa, i + j) ^ pw;
                         same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
                     } else { // past the bytes carried along: byte by byte, event first, then global memory
+                        const uint8_t *gb = c.bytes + (uint64_t)UN_GRP * lds32v(entry_sa + 36);
                         for (uint32_t b = 0; b < 4 && b < rem && same; b++) {
                             const uint32_t pos = i + j + b;
                             const uint32_t t = pos < 36 ? lds8v(entry_sa + pos) : (uint32_t)gb[pos];
@@ -300,16 +297,22 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_s
     }
 }
 
-// Resolve the warp's n pending events (n <= 32), one per lane.  carry = 1 + absolute position of the
-// last NUL byte seen in the events resolved so far by this warp (0 = none); returns the new carry.
+// Resolve the warp's n pending events (n <= 32).  carry = 1 + absolute position of the last NUL byte
+// seen in the events resolved so far by this warp (0 = none); returns the new carry.
+//
+// Phase 1, one event per lane: which start positions fired, where the NULs are, which packet(s) the
+// group lies in -> mask of candidate starts that are alive (inside the item, no NUL before them in their
+// packet) and mask of packet boundaries inside the group.
+// Phase 2, one alive candidate per lane, whichever event it came from: hash lookup and count.
 __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t q_sa, const uint32_t n, uint64_t carry,
                                               const uint32_t lutlane, const uint32_t mul)
 {
     const uint32_t lane = threadIdx.x & 31;
     __syncwarp();
     const uint32_t entry_sa = q_sa + lane * (UN_Q_WORDS * 4);
-    uint32_t cm = 0, zm = 0, item = 0, lo = 0;
-    uint64_t gq = 0; // absolute position of my group's first byte
+    uint32_t cm = 0, zm = 0;
+    uint64_t gq = 0, b_abs = 0, e_abs = 0; // my group's first byte; my item's byte range (absolute)
+    uint32_t ks = 0, ke = 0;
     if (lane < n) {
         uint32_t w[8];
         const uint4 a = lds128v(entry_sa), b = lds128v(entry_sa + 16), t = lds128v(entry_sa + 32);
@@ -317,9 +320,10 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
         w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
         const uint32_t la = t.x;
         gq = c.abs_base + (uint64_t)UN_GRP * t.y;
-        lo = t.z & 0xffu;
-        const uint32_t hi = t.z >> 8;
-        item = t.w;
+        ks = __ldg(c.items + t.w);
+        ke = __ldg(c.items + t.w + 1);
+        b_abs = __ldg(c.offsets + ks);
+        e_abs = __ldg(c.offsets + ke);
         // which of my 32 start positions fired (starts 0..31 report at bytes 3..34)
         uint32_t S, cmr = 0, na;
         S = LUT_AT(w[0], SEL0) & 0x808080ffu;
@@ -331,8 +335,11 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
         SV_WORD(w[5]); SV_WORD(w[6]); SV_WORD(w[7]);
         const uint32_t na32 = na; // NUL bit over bytes 0..31 only
         SV_STEP(la, SEL0); SV_STEP(la, SEL1); SV_STEP(la, SEL2);
+        // the item's first and last rows overhang it: starts count inside [b_abs, e_abs) only, and bytes
+        // past e_abs may be stale ring contents, so NULs count below e_abs only
+        const uint32_t lo = b_abs > gq ? (uint32_t)min(b_abs - gq, (uint64_t)32) : 0u;
+        const uint32_t hi = e_abs > gq ? (uint32_t)min(e_abs - gq, (uint64_t)32) : 0u;
         cm = __brev(cmr) & bit_window(lo, hi);
-        // stale bytes past the end of the item's last row are not text: NULs count below hi only
         if (na32 >> 31) zm = zero_mask32(w) & bit_window(0, hi);
     }
     // last NUL before my group: the nearest earlier event that holds one, else the warp's carry
@@ -344,35 +351,85 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
     const uint64_t from_top = __shfl_sync(FULL, mylast1, nulm ? 31 - __clz(nulm) : 0);
     if (nulm) carry = from_top;
 
+    uint32_t am = 0, bm = 0, nextb = 255; // alive candidates; packet starts inside the group (bit = offset);
+                                          // offset of the first packet start at or after the group's end
     if (cm) {
-        // the packet that holds my first valid start position: the last k in [ks, ke) with offsets[k] <= p0
-        const uint64_t p0 = gq + lo;
-        uint32_t k = __ldg(c.items + item), k1 = __ldg(c.items + item + 1);
+        // the packet that holds my first candidate: the last k in [ks, ke) with offsets[k] <= p0
+        const uint64_t p0 = gq + (__ffs(cm) - 1);
+        uint32_t k = ks, k1 = ke;
         while (k1 - k > 1) {
             const uint32_t mid = k + (k1 - k) / 2;
             if (__ldg(c.offsets + mid) <= p0) k = mid; else k1 = mid;
         }
         uint64_t ps = __ldg(c.offsets + k), pe = __ldg(c.offsets + k + 1);
-        do {
-            const uint32_t i = __ffs(cm) - 1;
-            cm &= cm - 1;
-            const uint64_t q = gq + i;
-            while (q >= pe) { // into the next packet (q lies inside the item, so one exists)
-                k++;
-                ps = pe;
-                pe = __ldg(c.offsets + k + 1);
-            }
-            const uint32_t zb = zm & ((1u << i) - 1u);
-            const uint64_t last1 = zb ? gq + (32u - __clz(zb)) : prev1;
-            if (last1 > ps) continue; // a NUL in [ps, q): kmp_matcher's strlen() stopped before q
-            const uint64_t room64 = pe - q;
-            const uint32_t room = room64 > 0xffffu ? 0xffffu : (uint32_t)room64;
-            if (c.vtab_in_smem) verify_start<true>(c, entry_sa, i, gq, room);
-            else verify_start<false>(c, entry_sa, i, gq, room);
-        } while (cm);
+        bool dead = prev1 > ps; // a NUL in [ps, group): kmp_matcher's strlen() stopped before my group
+        uint32_t a = ps > gq ? (uint32_t)(ps - gq) : 0u; // the packet [ps, pe) covers my group from offset a on
+        for (;;) {
+            const uint32_t b = pe - gq >= 32 ? 32u : (uint32_t)(pe - gq);
+            const uint32_t seg = bit_window(a, b), z = zm & seg;
+            if (!dead) am |= cm & seg & (z ? (z & (0u - z)) - 1u : FULL); // starts before the packet's first NUL
+            if (b == 32) break;
+            bm |= 1u << b;          // the next packet starts inside my group
+            if (k + 1 >= ke) break; // ... or the item ends there: nothing beyond is mine
+            a = b;
+            dead = false;
+            k++;
+            ps = pe;
+            pe = __ldg(c.offsets + k + 1);
+        }
+        nextb = pe - gq > 255 ? 255u : (uint32_t)(pe - gq);
+    }
+    // publish what phase 2 needs next to the event's bytes
+    if (lane < n) {
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(entry_sa + 40), "r"(bm), "r"(nextb) : "memory");
+    }
+    // alive candidates, numbered across the lanes
+    const uint32_t cnt = __popc(am);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    const uint32_t excl = incl - cnt;
+    __syncwarp();
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        // owner of candidate t: the first lane whose inclusive count exceeds t
+        uint32_t l = 0;
+#pragma unroll
+        for (uint32_t s = 16; s; s >>= 1) {
+            const uint32_t v = __shfl_sync(FULL, incl, l + s - 1);
+            if (v <= t) l += s;
+        }
+        l &= 31;
+        uint32_t m = __shfl_sync(FULL, am, l);
+        const uint32_t first = __shfl_sync(FULL, excl, l);
+        if (t < total) {
+            for (uint32_t j = first; j < t; j++) m &= m - 1;
+            const uint32_t i = __ffs(m) - 1;
+            const uint32_t owner_sa = q_sa + l * (UN_Q_WORDS * 4);
+            uint32_t obm, onext;
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(obm), "=r"(onext) : "r"(owner_sa + 40) : "memory");
+            const uint32_t above = obm & ~((2u << i) - 1u); // packet starts after byte i
+            const uint32_t room = (above ? (uint32_t)__ffs(above) - 1u : onext) - i;
+            if (c.vtab_in_smem) verify_start<true>(c, owner_sa, i, room);
+            else verify_start<false>(c, owner_sa, i, room);
+        }
     }
     __syncwarp();
     return carry;
+}
+
+// warp-uniform value, in a form the compiler can keep in a uniform register
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(FULL, v, 0); }
+__device__ __forceinline__ uint64_t uni(uint64_t v) { return __shfl_sync(FULL, v, 0); }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_constant__ union_params p)
@@ -395,7 +452,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     uint8_t *ring_all = lut + UN_LUT_BYTES;
     uint8_t *mbar_all = ring_all + UN_RING_BYTES;
     uint8_t *q_all = smem;
-    uint32_t *s_lut_saddr = reinterpret_cast<uint32_t *>(smem + UN_Q_BYTES);
+    uint8_t *scratch_all = smem + UN_Q_BYTES;
+    uint32_t *s_lut_saddr = reinterpret_cast<uint32_t *>(scratch_all + UN_SCRATCH_BYTES);
     uint32_t *s_counts = reinterpret_cast<uint32_t *>(s_lut_saddr + 4);
     uint32_t *s_vtab = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_counts) + counts_bytes);
 
@@ -407,7 +465,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         for (uint32_t i = threadIdx.x; i < p.vtab_words; i += UN_THREADS) s_vtab[i] = p.vtab[i];
     if (threadIdx.x == 0) *s_lut_saddr = dyn_saddr + lut_off;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t warp = uni(threadIdx.x >> 5);
     // per-warp row ring: UN_SLOTS slots of one row (+16 bytes) each, one mbarrier per slot
     const uint32_t ring_sa = saddr_of(ring_all) + warp * (UN_SLOTS * UN_SLOT_BYTES);
     const uint32_t mbar_sa = saddr_of(mbar_all) + warp * (8 * UN_SLOTS);
@@ -430,6 +488,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     sc.vtab_g = p.vtab;
     sc.vtab_sa = saddr_of(s_vtab);
     sc.vtab_in_smem = p.vtab_in_smem;
+    sc.scratch_sa = saddr_of(scratch_all) + warp * 128;
     sc.s_counts = p.counts_in_smem ? s_counts : nullptr;
     sc.g_counts = p.uniq_counts;
 
@@ -440,11 +499,11 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(&p.work[0], 1u);
-        item = __shfl_sync(FULL, item, 0);
+        item = uni(item);
         if (item >= p.n_items) break;
-        const uint32_t ks = p.items[item], ke = p.items[item + 1];
+        const uint32_t ks = uni(p.items[item]), ke = uni(p.items[item + 1]);
         if (ks >= ke) continue;
-        const uint64_t b_abs = p.offsets[ks], e_abs = p.offsets[ke];
+        const uint64_t b_abs = uni(p.offsets[ks]), e_abs = uni(p.offsets[ke]);
         if (b_abs == e_abs) continue;
         if (e_abs - b_abs >= (1ull << 31)) { // a packet over 2 GiB: outside the documented limits
             if (lane == 0) atomicOr(&p.work[1], 1u);
@@ -452,13 +511,13 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         }
         const uint64_t row0 = b_abs & ~127ull; // absolute position of the item's first row
         const uint8_t *text = p.bytes + (row0 - p.abs_base);
-        const int32_t b_rel = (int32_t)(b_abs - row0), e_rel = (int32_t)(e_abs - row0);
-        const uint32_t load_end = ((uint32_t)e_rel + 15u) & ~15u;
-        const uint32_t nrows = ((uint32_t)e_rel + UN_ROW - 1) / UN_ROW;
-        const uint32_t g32_0 = (uint32_t)((row0 - p.abs_base) >> 5) + lane;
+        const uint32_t e_rel = (uint32_t)(e_abs - row0);
+        const uint32_t load_end = (e_rel + 15u) & ~15u;
+        const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
+        uint32_t g32 = (uint32_t)((row0 - p.abs_base) >> 5) + lane; // my group's index in 32-byte units
 
         auto issue_row = [&](uint32_t r, uint32_t slot) {
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t row = r * UN_ROW;
                 const uint32_t nb = min(UN_SLOT_BYTES, load_end - row);
                 mbar_expect_tx(mbar_sa + 8 * slot, nb);
@@ -468,9 +527,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         for (uint32_t r = 0; r < UN_SLOTS && r < nrows; r++) issue_row(r, r);
 
         uint32_t slot = 0;
-        int32_t g = (int32_t)(lane * UN_GRP); // my group's first byte, relative to row0
 #pragma unroll 1
-        for (uint32_t r = 0; r < nrows; r++, g += (int32_t)UN_ROW) {
+        for (uint32_t r = 0; r < nrows; r++, g32 += 32) {
             mbar_wait(mbar_sa + 8 * slot, (ring_phase >> slot) & 1u);
             const uint32_t mine = ring_sa + slot * UN_SLOT_BYTES + lane * UN_GRP;
             const uint4 c0 = lds128v(mine), c1 = lds128v(mine + 16);
@@ -479,11 +537,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             // ---- shift-and filter over 35 bytes ---------------------------------------------------
             uint32_t S, accB, accC;
             S = LUT_AT(c0.x, SEL0) & 0x808080ffu; // no history: only the NUL stage is pre-armed
-#ifdef KMPB_UN_SUM_ACC
-            accB = S >> 24;
-#else
             accB = S;
-#endif
             SA_STEP(c0.x, SEL1, accB);
             SA_STEP(c0.x, SEL2, accB);
             SA_STEP(c0.x, SEL3, accB);
@@ -496,14 +550,10 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             SA_WORD(c1.w, accB);
             // lookahead: candidate starts 29..31 report here; a NUL here is the next lane's
             accC = 0;
-            SA_NEXT(la, SEL0); accC |= S;
-            SA_NEXT(la, SEL1); accC |= S;
-            SA_NEXT(la, SEL2); accC |= S;
-#ifdef KMPB_UN_SUM_ACC
-            const bool flag = (accB | (accC & 0x7f000000u)) != 0;
-#else
+            SA_STEP(la, SEL0, accC);
+            SA_STEP(la, SEL1, accC);
+            SA_STEP(la, SEL2, accC);
             const bool flag = ((accB & 0xff000000u) | (accC & 0x7f000000u)) != 0;
-#endif
             const uint32_t m = __ballot_sync(FULL, flag);
 
             // every lane holds its bytes: refill the slot with the row UN_SLOTS ahead
@@ -521,12 +571,10 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                     qn = 0;
                 }
                 if (flag) {
-                    // valid start positions of my group: [lo, hi) -- the item's first and last rows overhang it
-                    const int32_t lo = max(min(b_rel - g, 32), 0), hi = max(min(e_rel - g, 32), 0);
                     const uint32_t e = q_sa + (qn + __popc(m & lt)) * (UN_Q_WORDS * 4);
                     sts128v(e, c0.x, c0.y, c0.z, c0.w);
                     sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
-                    sts128v(e + 32, la, g32_0 + (r << 5), (uint32_t)lo | ((uint32_t)hi << 8), item);
+                    sts128v(e + 32, la, g32, 0u, item);
                 }
                 qn += n;
             }

@@ -267,7 +267,7 @@ static int build_dfa(kmpb_tables *t)
 
 /* ---- start-anchored verification tables ---------------------------------------------------------- */
 
-#define VT_HEADER 12
+#define VT_HEADER (12 + 64) /* 12 header words + 256 first-byte key-length masks, one byte each */
 #define VT_EMPTY 0xffffffffu
 
 uint32_t kmpb_vtab_hash(uint32_t key, uint32_t mask) { return ((key * 0x9e3779b1u) >> 12) & mask; }
@@ -324,6 +324,7 @@ static int build_verify_tables(kmpb_tables *t)
         rec[2] = VT_EMPTY;
         memcpy((uint8_t *)(v + blob_off + bw), p, len); /* rest of the last word stays zero */
         bw += (len + 3) / 4;
+        ((uint8_t *)(v + 12))[p[0]] |= (uint8_t)(1u << (L - 1));
         /* insert: same key -> chain (only possible for len >= 4; shorter patterns are distinct keys) */
         uint32_t s = kmpb_vtab_hash(key, slots[L] - 1);
         for (;;) {

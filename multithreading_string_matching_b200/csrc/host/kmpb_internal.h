@@ -55,6 +55,7 @@ typedef struct kmpb_tables {
      * Layout of vtab (u32 words):
      *   [0] total words   [1..4] word offset of table L (0 = none)   [5..8] slot mask of table L
      *   [9] word offset of the records   [10] word offset of the pattern words   [11] bit L-1 set when table L exists
+     *   [12..75] 256 bytes: byte b has bit L-1 set when some pattern with key length L starts with byte value b
      *   tables: slots of 2 words {key, first record or 0xffffffff}
      *   records (3 words per distinct pattern): {length, word offset of its bytes inside the pattern words,
      *            next record with the same 4-byte key or 0xffffffff}
