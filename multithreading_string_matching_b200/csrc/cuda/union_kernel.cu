@@ -155,6 +155,12 @@ __device__ __forceinline__ uint32_t lds8v(uint32_t saddr)
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ uint2 lds64(uint32_t saddr)
+{
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds32v(uint32_t saddr)
 {
     uint32_t v;
@@ -251,30 +257,40 @@ __device__ __forceinline__ void count_hit(const slow_ctx &c, uint32_t u)
     else atomicAdd(c.g_counts + u, 1ull);
 }
 
-// Every pattern that starts at byte `i` of the event at entry_sa (whose group starts at absolute byte
-// gq) and is at most `room` bytes long is counted.
+// Every pattern that starts at byte `i` of the event at entry_sa and is at most `room` (>= 1) bytes long
+// is counted.  One loop over the key lengths that occur for this first byte, so that lanes probing
+// different tables still run the same instructions.
 template <bool VS>
 __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_sa, uint32_t i, uint32_t room)
 {
     auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(c.vtab_sa + 4u * word) : __ldg(c.vtab_g + word); };
+    auto vt2 = [&](uint32_t word) -> uint2 {
+        return VS ? lds64(c.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(c.vtab_g + word));
+    };
     const uint32_t x0 = entry_window(entry_sa, i);
-    // key lengths of the patterns that start with this byte
+    // key lengths of the patterns that start with this byte, cut to what fits before the packet ends
     const uint32_t b0 = x0 & 0xffu;
-    const uint32_t lens = VS ? lds8v(c.vtab_sa + 48u + b0) : (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(c.vtab_g + 12) + b0);
+    uint32_t lens = VS ? lds8v(c.vtab_sa + 48u + b0) : (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(c.vtab_g + 12) + b0);
+    lens &= (2u << (room < 4 ? room - 1 : 3)) - 1u;
     if (lens == 0) return;
     const uint32_t rec0 = vt(9), pat0 = vt(10);
-#pragma unroll
-    for (uint32_t L = 1; L <= 4; L++) {
-        if (!((lens >> (L - 1)) & 1u) || L > room) continue;
-        const uint32_t key = L == 4 ? x0 : x0 & ((1u << (8 * L)) - 1u);
+    do {
+        const uint32_t L = __ffs(lens); // 1..4
+        lens &= lens - 1;
+        const uint32_t key = x0 & (0xffffffffu >> (32u - 8u * L));
         const uint32_t mask = vt(4 + L), tab0 = vt(L);
+        uint32_t u = 0xffffffffu;
         for (uint32_t slot = ((key * 0x9e3779b1u) >> 12) & mask;; slot = (slot + 1) & mask) {
-            const uint32_t ek = vt(tab0 + 2 * slot), ev = vt(tab0 + 2 * slot + 1);
-            if (ev == 0xffffffffu) break;
-            if (ek != key) continue;
-            for (uint32_t u = ev; u != 0xffffffffu; u = vt(rec0 + 3 * u + 2)) {
-                const uint32_t m = vt(rec0 + 3 * u), pw0 = pat0 + vt(rec0 + 3 * u + 1);
-                if (m > room) continue; // would end past the packet (serial.c:191: the text ends there)
+            const uint2 e = vt2(tab0 + 2 * slot);
+            if (e.y == 0xffffffffu) break;
+            if (e.x == key) {
+                u = e.y;
+                break;
+            }
+        }
+        while (u != 0xffffffffu) { // the patterns that share this key
+            const uint32_t m = vt(rec0 + 3 * u), pw0 = pat0 + vt(rec0 + 3 * u + 1), next = vt(rec0 + 3 * u + 2);
+            if (m <= room) { // else it would end past the packet (serial.c:191: the text ends there)
                 bool same = true;
                 for (uint32_t j = 4; j < m && same; j += 4) { // pattern bytes j..j+3 against text bytes i+j..
                     const uint32_t pw = vt(pw0 + (j >> 2)), rem = m - j;
@@ -292,9 +308,9 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_s
                 }
                 if (same) count_hit(c, u);
             }
-            break;
+            u = next;
         }
-    }
+    } while (lens);
 }
 
 // Resolve the warp's n pending events (n <= 32).  carry = 1 + absolute position of the last NUL byte
