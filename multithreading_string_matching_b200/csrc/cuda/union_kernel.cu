@@ -222,12 +222,17 @@ __device__ __forceinline__ uint32_t bit_window(uint32_t lo, uint32_t hi)
         SA_STEP(word, SEL2, acc); \
         SA_STEP(word, SEL3, acc); \
     } while (0)
-// same step, shifting "a candidate start fired" into cmr (the first step ends up in the highest bit)
+// same step, shifting "this byte is NUL" into zr (the first step ends up in the highest bit used) ...
+#define SZ_STEP(word, sel)                 \
+    do {                                   \
+        SA_NEXT(word, sel);                \
+        zr = __funnelshift_l(S, zr, 1);    \
+    } while (0)
+// ... and "a candidate start fired" into cmr
 #define SV_STEP(word, sel)                                              \
     do {                                                                \
-        SA_NEXT(word, sel);                                             \
+        SZ_STEP(word, sel);                                             \
         cmr = __funnelshift_l((S & 0x7f000000u) + 0x7f000000u, cmr, 1); \
-        na |= S;                                                        \
     } while (0)
 #define SV_WORD(word)        \
     do {                     \
@@ -268,9 +273,9 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_s
         return VS ? lds64(c.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(c.vtab_g + word));
     };
     const uint32_t x0 = entry_window(entry_sa, i);
-    // key lengths of the patterns that start with this byte, cut to what fits before the packet ends
-    const uint32_t b0 = x0 & 0xffu;
-    uint32_t lens = VS ? lds8v(c.vtab_sa + 48u + b0) : (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(c.vtab_g + 12) + b0);
+    // key lengths of the patterns that can start with these two bytes, cut to what fits before the packet ends
+    const uint32_t ls = ((x0 & 0xffffu) * 0x9e3779b1u) >> 22;
+    uint32_t lens = VS ? lds8v(c.vtab_sa + 48u + ls) : (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(c.vtab_g + 12) + ls);
     lens &= (2u << (room < 4 ? room - 1 : 3)) - 1u;
     if (lens == 0) return;
     const uint32_t rec0 = vt(9), pat0 = vt(10);
@@ -330,33 +335,36 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
     uint64_t gq = 0, b_abs = 0, e_abs = 0; // my group's first byte; my item's byte range (absolute)
     uint32_t ks = 0, ke = 0;
     if (lane < n) {
-        uint32_t w[8];
-        const uint4 a = lds128v(entry_sa), b = lds128v(entry_sa + 16), t = lds128v(entry_sa + 32);
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-        w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-        const uint32_t la = t.x;
+        const uint4 t = lds128v(entry_sa + 32); // lookahead, group index, quarter reports, item
         gq = c.abs_base + (uint64_t)UN_GRP * t.y;
         ks = __ldg(c.items + t.w);
         ke = __ldg(c.items + t.w + 1);
         b_abs = __ldg(c.offsets + ks);
         e_abs = __ldg(c.offsets + ke);
-        // which of my 32 start positions fired (starts 0..31 report at bytes 3..34)
-        uint32_t S, cmr = 0, na;
-        S = LUT_AT(w[0], SEL0) & 0x808080ffu;
-        na = S;
-        SA_NEXT(w[0], SEL1); na |= S;
-        SA_NEXT(w[0], SEL2); na |= S;
-        SV_STEP(w[0], SEL3);
-        SV_WORD(w[1]); SV_WORD(w[2]); SV_WORD(w[3]); SV_WORD(w[4]);
-        SV_WORD(w[5]); SV_WORD(w[6]); SV_WORD(w[7]);
-        const uint32_t na32 = na; // NUL bit over bytes 0..31 only
-        SV_STEP(la, SEL0); SV_STEP(la, SEL1); SV_STEP(la, SEL2);
+        // Re-run the filter over the quarters that reported, this time recording which start positions
+        // fired and which bytes are NUL.  Quarter k: bytes 8k..8k+10 (three bytes of run-in, then starts
+        // 8k..8k+7 report at bytes 8k+3..8k+10); the NUL bit is exact from the first byte on.
+        uint32_t quarters = ((((t.z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t.z) & 0x80808080u); // bit 8k+7: quarter k
+        while (quarters) {
+            const uint32_t k8 = (__ffs(quarters) - 1) & ~7u; // 8k
+            quarters &= quarters - 1;
+            const uint32_t w0 = lds32v(entry_sa + k8), w1 = lds32v(entry_sa + k8 + 4), w2 = lds32v(entry_sa + k8 + 8);
+            uint32_t S, cmr = 0, zr;
+            S = LUT_AT(w0, SEL0) & 0x808080ffu;
+            zr = S >> 31;
+            SZ_STEP(w0, SEL1); SZ_STEP(w0, SEL2);
+            SV_STEP(w0, SEL3);
+            SV_WORD(w1);
+            SV_STEP(w2, SEL0); SV_STEP(w2, SEL1); SV_STEP(w2, SEL2);
+            cm |= (__brev(cmr) >> 24) << k8;
+            zm |= (__brev(zr) >> 21) << k8;
+        }
         // the item's first and last rows overhang it: starts count inside [b_abs, e_abs) only, and bytes
         // past e_abs may be stale ring contents, so NULs count below e_abs only
         const uint32_t lo = b_abs > gq ? (uint32_t)min(b_abs - gq, (uint64_t)32) : 0u;
         const uint32_t hi = e_abs > gq ? (uint32_t)min(e_abs - gq, (uint64_t)32) : 0u;
-        cm = __brev(cmr) & bit_window(lo, hi);
-        if (na32 >> 31) zm = zero_mask32(w) & bit_window(0, hi);
+        cm &= bit_window(lo, hi);
+        zm &= bit_window(0, hi);
     }
     // last NUL before my group: the nearest earlier event that holds one, else the warp's carry
     const uint64_t mylast1 = zm ? gq + (32u - __clz(zm)) : 0ull; // 1 + position of my last NUL
@@ -551,25 +559,42 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             const uint32_t la = lds32v(mine + UN_GRP);
 
             // ---- shift-and filter over 35 bytes ---------------------------------------------------
-            uint32_t S, accB, accC;
+            // Reports are collected per quarter of the group: acc[k] covers the steps at which starts
+            // 8k..8k+7 report (and, for k = 0, the three steps before them, for their NUL bits).
+            uint32_t S, acc0, acc1, acc2, acc3, accC;
             S = LUT_AT(c0.x, SEL0) & 0x808080ffu; // no history: only the NUL stage is pre-armed
-            accB = S;
-            SA_STEP(c0.x, SEL1, accB);
-            SA_STEP(c0.x, SEL2, accB);
-            SA_STEP(c0.x, SEL3, accB);
-            SA_WORD(c0.y, accB);
-            SA_WORD(c0.z, accB);
-            SA_WORD(c0.w, accB);
-            SA_WORD(c1.x, accB);
-            SA_WORD(c1.y, accB);
-            SA_WORD(c1.z, accB);
-            SA_WORD(c1.w, accB);
+            acc0 = S;
+            SA_STEP(c0.x, SEL1, acc0);
+            SA_STEP(c0.x, SEL2, acc0);
+            SA_STEP(c0.x, SEL3, acc0);
+            SA_WORD(c0.y, acc0);
+            SA_STEP(c0.z, SEL0, acc0);
+            SA_STEP(c0.z, SEL1, acc0);
+            SA_STEP(c0.z, SEL2, acc0);
+            acc1 = 0;
+            SA_STEP(c0.z, SEL3, acc1);
+            SA_WORD(c0.w, acc1);
+            SA_STEP(c1.x, SEL0, acc1);
+            SA_STEP(c1.x, SEL1, acc1);
+            SA_STEP(c1.x, SEL2, acc1);
+            acc2 = 0;
+            SA_STEP(c1.x, SEL3, acc2);
+            SA_WORD(c1.y, acc2);
+            SA_STEP(c1.z, SEL0, acc2);
+            SA_STEP(c1.z, SEL1, acc2);
+            SA_STEP(c1.z, SEL2, acc2);
+            acc3 = 0;
+            SA_STEP(c1.z, SEL3, acc3);
+            SA_WORD(c1.w, acc3);
             // lookahead: candidate starts 29..31 report here; a NUL here is the next lane's
             accC = 0;
             SA_STEP(la, SEL0, accC);
             SA_STEP(la, SEL1, accC);
             SA_STEP(la, SEL2, accC);
-            const bool flag = ((accB & 0xff000000u) | (accC & 0x7f000000u)) != 0;
+            acc3 |= accC & 0x7f000000u;
+            // the four top bytes side by side: quarter k has something to resolve iff byte k is nonzero
+            const uint32_t tops = __byte_perm(__byte_perm(acc0, acc1, 0x0073), __byte_perm(acc2, acc3, 0x0073), 0x5410);
+            const bool flag = tops != 0;
             const uint32_t m = __ballot_sync(FULL, flag);
 
             // every lane holds its bytes: refill the slot with the row UN_SLOTS ahead
@@ -590,7 +615,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                     const uint32_t e = q_sa + (qn + __popc(m & lt)) * (UN_Q_WORDS * 4);
                     sts128v(e, c0.x, c0.y, c0.z, c0.w);
                     sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
-                    sts128v(e + 32, la, g32, 0u, item);
+                    sts128v(e + 32, la, g32, tops, item);
                 }
                 qn += n;
             }

@@ -267,10 +267,14 @@ static int build_dfa(kmpb_tables *t)
 
 /* ---- start-anchored verification tables ---------------------------------------------------------- */
 
-#define VT_HEADER (12 + 64) /* 12 header words + 256 first-byte key-length masks, one byte each */
+#define VT_LENS_SLOTS 1024 /* key-length masks, one byte per hash slot of a pattern's first two bytes */
+#define VT_HEADER (12 + VT_LENS_SLOTS / 4)
 #define VT_EMPTY 0xffffffffu
 
 uint32_t kmpb_vtab_hash(uint32_t key, uint32_t mask) { return ((key * 0x9e3779b1u) >> 12) & mask; }
+
+/* slot of a text position's first two bytes (little-endian u16) in the key-length masks */
+uint32_t kmpb_vtab_lens_slot(uint32_t first2) { return ((first2 & 0xffffu) * 0x9e3779b1u) >> 22; }
 
 /* first min(len,4) bytes of a pattern as a little-endian word */
 static uint32_t key_of(const uint8_t *p, uint32_t len)
@@ -293,7 +297,7 @@ static int build_verify_tables(kmpb_tables *t)
     for (uint32_t L = 1; L <= 4; L++) {
         if (count[L] == 0) continue;
         uint32_t n = 8;
-        while (n < 2 * count[L]) n *= 2; /* load factor <= 0.5: short probe sequences */
+        while (n < 4 * count[L]) n *= 2; /* load factor <= 0.25: short probe sequences */
         if (n > (1u << 20)) return kmpb_fail(KMPB_ELIMIT, "too many patterns for the verification tables");
         slots[L] = n;
         toff[L] = at;
@@ -324,7 +328,9 @@ static int build_verify_tables(kmpb_tables *t)
         rec[2] = VT_EMPTY;
         memcpy((uint8_t *)(v + blob_off + bw), p, len); /* rest of the last word stays zero */
         bw += (len + 3) / 4;
-        ((uint8_t *)(v + 12))[p[0]] |= (uint8_t)(1u << (L - 1));
+        /* which key lengths can start with these two bytes (a 1-byte pattern: any second byte) */
+        if (len >= 2) ((uint8_t *)(v + 12))[kmpb_vtab_lens_slot(p[0] | (uint32_t)p[1] << 8)] |= (uint8_t)(1u << (L - 1));
+        else for (uint32_t b1 = 0; b1 < 256; b1++) ((uint8_t *)(v + 12))[kmpb_vtab_lens_slot(p[0] | b1 << 8)] |= 1u;
         /* insert: same key -> chain (only possible for len >= 4; shorter patterns are distinct keys) */
         uint32_t s = kmpb_vtab_hash(key, slots[L] - 1);
         for (;;) {

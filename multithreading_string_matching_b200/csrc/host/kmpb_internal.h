@@ -55,7 +55,8 @@ typedef struct kmpb_tables {
      * Layout of vtab (u32 words):
      *   [0] total words   [1..4] word offset of table L (0 = none)   [5..8] slot mask of table L
      *   [9] word offset of the records   [10] word offset of the pattern words   [11] bit L-1 set when table L exists
-     *   [12..75] 256 bytes: byte b has bit L-1 set when some pattern with key length L starts with byte value b
+     *   [12..267] 1024 bytes: byte kmpb_vtab_lens_slot(first two text bytes) has bit L-1 set when some pattern with
+     *            key length L starts with those two bytes (a 1-byte pattern: with that byte)
      *   tables: slots of 2 words {key, first record or 0xffffffff}
      *   records (3 words per distinct pattern): {length, word offset of its bytes inside the pattern words,
      *            next record with the same 4-byte key or 0xffffffff}
@@ -67,6 +68,7 @@ typedef struct kmpb_tables {
 
 /* slot of `key` in a verification table with `mask`+1 slots (the device uses the same expression) */
 uint32_t kmpb_vtab_hash(uint32_t key, uint32_t mask);
+uint32_t kmpb_vtab_lens_slot(uint32_t first2);
 int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat);
 void kmpb_tables_free(kmpb_tables *t);
 

@@ -84,7 +84,7 @@ static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int
             for (int k = 0; k < 4; k++) x0 |= (uint32_t)text[s + k] << (8 * k); /* text is zero padded */
             for (uint32_t L = 1; L <= 4; L++) {
                 if (!((v[11] >> (L - 1)) & 1u)) continue;
-                if (!((((const uint8_t *)(v + 12))[x0 & 0xffu] >> (L - 1)) & 1u)) continue; /* first-byte mask, as the device probes */
+                if (!((((const uint8_t *)(v + 12))[kmpb_vtab_lens_slot(x0)] >> (L - 1)) & 1u)) continue; /* key-length mask, as the device probes */
                 const uint32_t key = L == 4 ? x0 : x0 & ((1u << (8 * L)) - 1u), mask = v[4 + L];
                 for (uint32_t slot = kmpb_vtab_hash(key, mask);; slot = (slot + 1) & mask) {
                     const uint32_t *e = v + v[L] + 2 * slot;
