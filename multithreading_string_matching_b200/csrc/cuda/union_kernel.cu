@@ -136,6 +136,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar_sa, uint32_t parity)
                  "}" ::"r"(mbar_sa), "r"(parity)
                  : "memory");
 }
+// per-lane 16-byte asynchronous copies (LDGSTS): the alternative row transport, KMPB_UN_LDGSTS
+__device__ __forceinline__ void cp_async16(uint32_t dst_sa, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ uint4 lds128v(uint32_t saddr)
 {
     uint4 v;
@@ -502,7 +513,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     // read back through shared memory so that no LUT load can be scheduled above the barrier
     const uint32_t lutlane = *s_lut_saddr + (lane << 2);
     const uint32_t mul = p.mul256;
-    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     const uint32_t q_sa = saddr_of(q_all) + warp * (UN_QCAP * UN_Q_WORDS * 4);
     slow_ctx sc;
     sc.bytes = p.bytes;
@@ -540,6 +552,26 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
         uint32_t g32 = (uint32_t)((row0 - p.abs_base) >> 5) + lane; // my group's index in 32-byte units
 
+#ifdef KMPB_UN_LDGSTS
+        // every lane copies its own 32 bytes (lane 0 also the 16 bytes after the row); one commit group per
+        // call, also when there is nothing left to copy, so that "all but the newest UN_SLOTS-1 groups are
+        // complete" always means "the row about to be scanned has arrived"
+        auto issue_row = [&](uint32_t r, uint32_t slot) {
+            const uint32_t row = r * UN_ROW, g = row + lane * UN_GRP;
+            const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES + lane * UN_GRP;
+            if (row + UN_SLOT_BYTES <= load_end) {
+                cp_async16(dst, text + g);
+                cp_async16(dst + 16, text + g + 16);
+                if (lane == 0) cp_async16(dst + UN_ROW, text + row + UN_ROW);
+            } else if (r < nrows) {
+                if (g < load_end) cp_async16(dst, text + g);
+                if (g + 16 < load_end) cp_async16(dst + 16, text + g + 16);
+                if (lane == 0 && row + UN_ROW < load_end) cp_async16(dst + UN_ROW, text + row + UN_ROW);
+            }
+            cp_async_commit();
+        };
+        for (uint32_t r = 0; r < UN_SLOTS; r++) issue_row(r, r);
+#else
         auto issue_row = [&](uint32_t r, uint32_t slot) {
             if (elect_one()) {
                 const uint32_t row = r * UN_ROW;
@@ -549,11 +581,17 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             }
         };
         for (uint32_t r = 0; r < UN_SLOTS && r < nrows; r++) issue_row(r, r);
+#endif
 
         uint32_t slot = 0;
 #pragma unroll 1
         for (uint32_t r = 0; r < nrows; r++, g32 += 32) {
+#ifdef KMPB_UN_LDGSTS
+            cp_async_wait<UN_SLOTS - 1>();
+            __syncwarp(); // my lookahead is the next lane's copy
+#else
             mbar_wait(mbar_sa + 8 * slot, (ring_phase >> slot) & 1u);
+#endif
             const uint32_t mine = ring_sa + slot * UN_SLOT_BYTES + lane * UN_GRP;
             const uint4 c0 = lds128v(mine), c1 = lds128v(mine + 16);
             const uint32_t la = lds32v(mine + UN_GRP);
@@ -598,8 +636,12 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             const uint32_t m = __ballot_sync(FULL, flag);
 
             // every lane holds its bytes: refill the slot with the row UN_SLOTS ahead
+#ifdef KMPB_UN_LDGSTS
+            issue_row(r + UN_SLOTS, slot);
+#else
             ring_phase ^= 1u << slot;
             if (r + UN_SLOTS < nrows) issue_row(r + UN_SLOTS, slot);
+#endif
             slot = slot + 1 == UN_SLOTS ? 0 : slot + 1;
 
 #ifdef KMPB_ABLATE_SLOW_PATH // measurement only (wrong counts): how fast is the fast path alone?
