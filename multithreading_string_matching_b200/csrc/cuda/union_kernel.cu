@@ -38,13 +38,13 @@
 #include "kmpb_device.cuh"
 
 #ifndef KMPB_UN_THREADS
-#define KMPB_UN_THREADS 640
+#define KMPB_UN_THREADS 896
 #endif
 #ifndef KMPB_UN_ITEM_KB
 #define KMPB_UN_ITEM_KB 64
 #endif
 #ifndef KMPB_UN_SLOTS
-#define KMPB_UN_SLOTS 3
+#define KMPB_UN_SLOTS 2
 #endif
 constexpr int UN_THREADS = KMPB_UN_THREADS; // one block per SM
 constexpr int UN_WARPS = UN_THREADS / 32;
@@ -136,7 +136,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar_sa, uint32_t parity)
                  "}" ::"r"(mbar_sa), "r"(parity)
                  : "memory");
 }
-// per-lane 16-byte asynchronous copies (LDGSTS): the alternative row transport, KMPB_UN_LDGSTS
+// per-lane 16-byte asynchronous copies global -> shared (SASS LDGSTS), completion by commit groups: the
+// default row transport (the TMA ring above is kept behind KMPB_UN_TMA; it measured 3 % slower)
 __device__ __forceinline__ void cp_async16(uint32_t dst_sa, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa), "l"(src) : "memory");
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
         uint32_t g32 = (uint32_t)((row0 - p.abs_base) >> 5) + lane; // my group's index in 32-byte units
 
-#ifdef KMPB_UN_LDGSTS
+#ifndef KMPB_UN_TMA
         // every lane copies its own 32 bytes (lane 0 also the 16 bytes after the row); one commit group per
         // call, also when there is nothing left to copy, so that "all but the newest UN_SLOTS-1 groups are
         // complete" always means "the row about to be scanned has arrived"
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         uint32_t slot = 0;
 #pragma unroll 1
         for (uint32_t r = 0; r < nrows; r++, g32 += 32) {
-#ifdef KMPB_UN_LDGSTS
+#ifndef KMPB_UN_TMA
             cp_async_wait<UN_SLOTS - 1>();
             __syncwarp(); // my lookahead is the next lane's copy
 #else
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             const uint32_t m = __ballot_sync(FULL, flag);
 
             // every lane holds its bytes: refill the slot with the row UN_SLOTS ahead
-#ifdef KMPB_UN_LDGSTS
+#ifndef KMPB_UN_TMA
             issue_row(r + UN_SLOTS, slot);
 #else
             ring_phase ^= 1u << slot;
