@@ -64,11 +64,10 @@ constexpr uint32_t FULL = 0xffffffffu;
 // the LUT.
 constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_WORDS * 4;
 constexpr uint32_t UN_RING_BYTES = UN_WARPS * UN_SLOTS * UN_SLOT_BYTES;
-constexpr uint32_t UN_MBAR_BYTES = UN_WARPS * 8 * UN_SLOTS;
 constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
 constexpr uint32_t UN_FRONT_FIXED = UN_Q_BYTES + UN_SCRATCH_BYTES + 16;
 constexpr uint32_t UN_FRONT_MAX = 60 * 1024; // what the gap is trusted to hold
-constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_RING_BYTES + UN_MBAR_BYTES;
+constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_RING_BYTES;
 static_assert(UN_FRONT_FIXED + 1024 <= UN_FRONT_MAX, "event lists do not fit in front of the LUT");
 static_assert(UN_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -111,33 +110,7 @@ __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets
 }
 
 // ---- helpers -----------------------------------------------------------------------------------
-// TMA (1-D bulk copy) + mbarrier: global -> shared without registers
-__device__ __forceinline__ void mbar_init(uint32_t mbar_sa, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_sa), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar_sa, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst_sa, const void *src, uint32_t bytes, uint32_t mbar_sa)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_sa),
-                 "l"(src), "r"(bytes), "r"(mbar_sa)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t mbar_sa, uint32_t parity)
-{
-    asm volatile("{\n\t"
-                 ".reg .pred p;\n\t"
-                 "KMPB_WAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@!p bra KMPB_WAIT_%=;\n\t"
-                 "}" ::"r"(mbar_sa), "r"(parity)
-                 : "memory");
-}
-// per-lane 16-byte asynchronous copies global -> shared (SASS LDGSTS), completion by commit groups: the
-// default row transport (the TMA ring above is kept behind KMPB_UN_TMA; it measured 3 % slower)
+// per-lane 16-byte asynchronous copies global -> shared (SASS LDGSTS), completion by commit groups
 __device__ __forceinline__ void cp_async16(uint32_t dst_sa, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa), "l"(src) : "memory");
@@ -461,13 +434,6 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
 // warp-uniform value, in a form the compiler can keep in a uniform register
 __device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(FULL, v, 0); }
 __device__ __forceinline__ uint64_t uni(uint64_t v) { return __shfl_sync(FULL, v, 0); }
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
 __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_constant__ union_params p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -479,14 +445,13 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     const uint32_t counts_bytes = p.counts_in_smem ? ((4u * p.n_uniq + 15u) & ~15u) : 0u;
     const uint32_t vtab_bytes = p.vtab_in_smem ? 4u * p.vtab_words : 0u;
     const uint32_t front_bytes = UN_FRONT_FIXED + counts_bytes + vtab_bytes;
-    if (lut_off < front_bytes || lut_off + UN_LUT_BYTES + UN_RING_BYTES + UN_MBAR_BYTES > dyn_size) {
+    if (lut_off < front_bytes || lut_off + UN_LUT_BYTES + UN_RING_BYTES > dyn_size) {
         // unexpected shared-memory window base: refuse rather than compute something wrong
         if (threadIdx.x == 0) atomicOr(&p.work[1], 2u);
         return;
     }
     uint8_t *lut = smem + lut_off;
     uint8_t *ring_all = lut + UN_LUT_BYTES;
-    uint8_t *mbar_all = ring_all + UN_RING_BYTES;
     uint8_t *q_all = smem;
     uint8_t *scratch_all = smem + UN_Q_BYTES;
     uint32_t *s_lut_saddr = reinterpret_cast<uint32_t *>(scratch_all + UN_SCRATCH_BYTES);
@@ -502,13 +467,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     if (threadIdx.x == 0) *s_lut_saddr = dyn_saddr + lut_off;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = uni(threadIdx.x >> 5);
-    // per-warp row ring: UN_SLOTS slots of one row (+16 bytes) each, one mbarrier per slot
+    // per-warp row ring: UN_SLOTS slots of one row (+16 bytes) each; my lookahead word is the first word
+    // of the next lane's chunk 0 (lane 31: of the tail)
     const uint32_t ring_sa = saddr_of(ring_all) + warp * (UN_SLOTS * UN_SLOT_BYTES);
-    const uint32_t mbar_sa = saddr_of(mbar_all) + warp * (8 * UN_SLOTS);
-    if (lane == 0) {
-        for (uint32_t s = 0; s < UN_SLOTS; s++) mbar_init(mbar_sa + 8 * s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
 
     // read back through shared memory so that no LUT load can be scheduled above the barrier
@@ -531,7 +492,6 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
 
     uint32_t qn = 0;         // pending events
     uint64_t carry = 0;      // 1 + position of the last NUL among the events resolved so far
-    uint32_t ring_phase = 0; // bit s = parity of slot s's mbarrier phase that the next wait completes
 
     for (;;) {
         uint32_t item = 0;
@@ -553,10 +513,11 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
         uint32_t g32 = (uint32_t)((row0 - p.abs_base) >> 5) + lane; // my group's index in 32-byte units
 
-#ifndef KMPB_UN_TMA
-        // every lane copies its own 32 bytes (lane 0 also the 16 bytes after the row); one commit group per
-        // call, also when there is nothing left to copy, so that "all but the newest UN_SLOTS-1 groups are
-        // complete" always means "the row about to be scanned has arrived"
+        // Every lane copies its own 32 bytes (lane 0 also the 16 bytes after the row) with 16-byte
+        // asynchronous copies.  One commit group per call, also when there is nothing left to copy, so
+        // that "all but the newest UN_SLOTS-1 groups are complete" always means "the row about to be
+        // scanned has arrived".  (A chunk-major slot layout, free of bank conflicts on both sides, measured
+        // 14 % slower on the fast path alone.)
         auto issue_row = [&](uint32_t r, uint32_t slot) {
             const uint32_t row = r * UN_ROW, g = row + lane * UN_GRP;
             const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES + lane * UN_GRP;
@@ -572,30 +533,15 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             cp_async_commit();
         };
         for (uint32_t r = 0; r < UN_SLOTS; r++) issue_row(r, r);
-#else
-        auto issue_row = [&](uint32_t r, uint32_t slot) {
-            if (elect_one()) {
-                const uint32_t row = r * UN_ROW;
-                const uint32_t nb = min(UN_SLOT_BYTES, load_end - row);
-                mbar_expect_tx(mbar_sa + 8 * slot, nb);
-                bulk_load(ring_sa + slot * UN_SLOT_BYTES, text + row, nb, mbar_sa + 8 * slot);
-            }
-        };
-        for (uint32_t r = 0; r < UN_SLOTS && r < nrows; r++) issue_row(r, r);
-#endif
 
         uint32_t slot = 0;
 #pragma unroll 1
         for (uint32_t r = 0; r < nrows; r++, g32 += 32) {
-#ifndef KMPB_UN_TMA
             cp_async_wait<UN_SLOTS - 1>();
             __syncwarp(); // my lookahead is the next lane's copy
-#else
-            mbar_wait(mbar_sa + 8 * slot, (ring_phase >> slot) & 1u);
-#endif
-            const uint32_t mine = ring_sa + slot * UN_SLOT_BYTES + lane * UN_GRP;
-            const uint4 c0 = lds128v(mine), c1 = lds128v(mine + 16);
-            const uint32_t la = lds32v(mine + UN_GRP);
+            const uint32_t base = ring_sa + slot * UN_SLOT_BYTES;
+            const uint4 c0 = lds128v(base + lane * UN_GRP), c1 = lds128v(base + lane * UN_GRP + 16);
+            const uint32_t la = lds32v(base + lane * UN_GRP + UN_GRP);
 
             // ---- shift-and filter over 35 bytes ---------------------------------------------------
             // Reports are collected per quarter of the group: acc[k] covers the steps at which starts
@@ -637,12 +583,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             const uint32_t m = __ballot_sync(FULL, flag);
 
             // every lane holds its bytes: refill the slot with the row UN_SLOTS ahead
-#ifndef KMPB_UN_TMA
             issue_row(r + UN_SLOTS, slot);
-#else
-            ring_phase ^= 1u << slot;
-            if (r + UN_SLOTS < nrows) issue_row(r + UN_SLOTS, slot);
-#endif
             slot = slot + 1 == UN_SLOTS ? 0 : slot + 1;
 
 #ifdef KMPB_ABLATE_SLOW_PATH // measurement only (wrong counts): how fast is the fast path alone?
