@@ -467,9 +467,16 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     if (threadIdx.x == 0) *s_lut_saddr = dyn_saddr + lut_off;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = uni(threadIdx.x >> 5);
-    // per-warp row ring: UN_SLOTS slots of one row (+16 bytes) each; my lookahead word is the first word
-    // of the next lane's chunk 0 (lane 31: of the tail)
+    // per-warp row ring: UN_SLOTS slots of one row (+16 bytes) each
+    // Inside a slot lane l owns bytes [32 l, 32 l + 32); lanes 4..7, 12..15, ... keep their two 16-byte
+    // halves swapped, which makes the 16-byte copies and reads of a quarter-warp hit 8 different bank groups.
     const uint32_t ring_sa = saddr_of(ring_all) + warp * (UN_SLOTS * UN_SLOT_BYTES);
+#ifdef KMPB_UN_NOSWIZZLE
+    const uint32_t off0 = lane * UN_GRP, off1 = off0 + 16, offla = off0 + UN_GRP;
+#else
+    const uint32_t off0 = lane * UN_GRP + ((lane >> 2) & 1u) * 16, off1 = off0 ^ 16u;
+    const uint32_t offla = lane == 31 ? UN_ROW : (lane + 1) * UN_GRP + (((lane + 1) >> 2) & 1u) * 16;
+#endif
     __syncthreads();
 
     // read back through shared memory so that no LUT load can be scheduled above the barrier
@@ -520,14 +527,14 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         // 14 % slower on the fast path alone.)
         auto issue_row = [&](uint32_t r, uint32_t slot) {
             const uint32_t row = r * UN_ROW, g = row + lane * UN_GRP;
-            const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES + lane * UN_GRP;
+            const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES;
             if (row + UN_SLOT_BYTES <= load_end) {
-                cp_async16(dst, text + g);
-                cp_async16(dst + 16, text + g + 16);
+                cp_async16(dst + off0, text + g);
+                cp_async16(dst + off1, text + g + 16);
                 if (lane == 0) cp_async16(dst + UN_ROW, text + row + UN_ROW);
             } else if (r < nrows) {
-                if (g < load_end) cp_async16(dst, text + g);
-                if (g + 16 < load_end) cp_async16(dst + 16, text + g + 16);
+                if (g < load_end) cp_async16(dst + off0, text + g);
+                if (g + 16 < load_end) cp_async16(dst + off1, text + g + 16);
                 if (lane == 0 && row + UN_ROW < load_end) cp_async16(dst + UN_ROW, text + row + UN_ROW);
             }
             cp_async_commit();
@@ -540,8 +547,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             cp_async_wait<UN_SLOTS - 1>();
             __syncwarp(); // my lookahead is the next lane's copy
             const uint32_t base = ring_sa + slot * UN_SLOT_BYTES;
-            const uint4 c0 = lds128v(base + lane * UN_GRP), c1 = lds128v(base + lane * UN_GRP + 16);
-            const uint32_t la = lds32v(base + lane * UN_GRP + UN_GRP);
+            const uint4 c0 = lds128v(base + off0), c1 = lds128v(base + off1);
+            const uint32_t la = lds32v(base + offla);
 
             // ---- shift-and filter over 35 bytes ---------------------------------------------------
             // Reports are collected per quarter of the group: acc[k] covers the steps at which starts
