@@ -4,41 +4,49 @@
 //
 //  FAST PATH (every byte) knows nothing about packets.  A warp streams work items -- runs of whole
 //  packets, ~64 KB of the flat CSR byte buffer -- in rows of 1024 contiguous bytes.  Rows travel
-//  global -> shared memory by TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a per-warp ring of
-//  UN_SLOTS slots, each completing on its own mbarrier; a slot holds the row plus the 16 bytes after it,
-//  so every lane finds its lookahead in its own slot.  Each lane pushes its 32 bytes (+3 bytes of
-//  lookahead) through a 4-byte-deep shift-and filter over 8 buckets:
+//  global -> shared memory by per-lane 16-byte asynchronous copies (cp.async, SASS LDGSTS) into a
+//  per-warp ring of UN_SLOTS slots, one commit group per row; a slot holds the row plus the 16 bytes
+//  after it, so every lane finds its lookahead in its own slot.  Each lane pushes its 32 bytes (+3
+//  bytes of lookahead) through a 4-byte-deep shift-and filter over 8 buckets:
 //      S = ((S << 8) | 0xff) & filter[byte]
 //  filter[] lives in shared memory in a bank-private layout (byte address = byte*256 + lane*4) at a
 //  64 KB-aligned shared address, so the one lookup per byte never bank-conflicts and its complete
 //  address is a single PRMT of the text word with a per-lane constant.  The shift-or-0xff is one
 //  integer multiply-add (FMA pipe), the AND one LOP3 (ALU pipe).  Bits 24..30 of S say "the last 4
 //  bytes are the first 4 bytes (or all the bytes) of some pattern of bucket b"; bit 31 says "this
-//  byte is NUL".  A lane whose 32 positions raised any of those bits appends an EVENT -- its 36 bytes
-//  and where they are -- to the warp's list in shared memory.  That is all: one ballot and (usually)
-//  a few stores per row on top of the filter.
+//  byte is NUL".  The reports are OR-ed per quarter of the group (8 start positions); a lane with any
+//  report appends an EVENT -- its 36 bytes, where they are, and which quarters reported -- to the warp's
+//  list in shared memory.  That is all: one ballot and (usually) a few stores per row on top of the
+//  filter.
 //
-//  SLOW PATH (events only).  When the list cannot take the next row's events the warp resolves 32 of
-//  them at once, one per lane, in stream order:
-//    - the lane re-runs the filter over its 36 bytes, this time recording which start positions fired
-//      and where the NUL bytes are;
-//    - it finds the packet that holds its group by binary search in the item's slice of `offsets`;
+//  SLOW PATH (events only).  When the list cannot take the next row's events the warp resolves up to 32
+//  of them at once, in stream order.
+//  Phase 1, one event per lane:
+//    - the lane re-runs the filter over the quarters that reported, this time recording which start
+//      positions fired and which bytes are NUL;
+//    - it finds the packet that holds its first candidate by binary search in its item's slice of
+//      `offsets`;
 //    - a candidate start q in packet [ps, pe) is alive when no NUL lies in [ps, q) -- the reference's
 //      "text ends at the first NUL" rule (serial.c:191).  NULs inside the group come from the lane's own
 //      mask; the last NUL before the group comes from the nearest earlier event that held one (events
-//      are in stream order, every NUL byte of the stream raises one) or from the warp's carry;
-//    - every alive candidate is looked up in the start-anchored hash tables of automaton.c (first
-//      min(len,4) bytes -> pattern records, remaining bytes compared word by word) and counted when it
-//      ends inside its packet (q + len <= pe).
+//      are in stream order, every NUL byte of the stream raises one) or from the warp's carry.
+//  Phase 2, one alive candidate per lane, whichever event it came from (they are numbered across the
+//  lanes by a prefix sum): it is looked up in the start-anchored hash tables of automaton.c (first
+//  min(len,4) bytes -> pattern records, remaining bytes compared word by word) and counted when it ends
+//  inside its packet (q + len <= pe).
 //  So every pattern occurrence that lies inside one packet and has no NUL before it in that packet is
 //  counted exactly once.  Counts go to shared-memory counters and leave the block as one atomic per
 //  distinct pattern.  No separators, no padding and no second pass over the payload.
+//
+//  Measured and dropped: a TMA bulk-copy ring (1 KB cp.async.bulk per row, 3 % slower:
+//  ~25 instructions per row to issue one copy from one elected lane), direct 16-byte loads with an L2
+//  prefetch (10 % slower: exposed latency), 64 bytes per lane (17 % slower), a chunk-major slot layout.
 #include <algorithm>
 
 #include "kmpb_device.cuh"
 
 #ifndef KMPB_UN_THREADS
-#define KMPB_UN_THREADS 896
+#define KMPB_UN_THREADS 1024
 #endif
 #ifndef KMPB_UN_ITEM_KB
 #define KMPB_UN_ITEM_KB 64
@@ -50,18 +58,17 @@ constexpr int UN_THREADS = KMPB_UN_THREADS; // one block per SM
 constexpr int UN_WARPS = UN_THREADS / 32;
 constexpr uint32_t UN_GRP = 32;                           // bytes per lane per row
 constexpr uint32_t UN_ROW = 32 * UN_GRP;                  // bytes per warp row
-constexpr uint32_t UN_SLOTS = KMPB_UN_SLOTS;              // rows in flight per warp (TMA -> shared memory)
+constexpr uint32_t UN_SLOTS = KMPB_UN_SLOTS;              // rows in flight per warp (cp.async -> shared memory)
 constexpr uint32_t UN_SLOT_BYTES = UN_ROW + 16;           // a row and the 16 bytes after it (lookahead)
 constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item size
 constexpr uint32_t UN_QCAP = 32;                          // events per warp list
-constexpr uint32_t UN_Q_WORDS = 12; // event: 32 B group, 4 B lookahead, group index, valid window, item (48 B)
+constexpr uint32_t UN_Q_WORDS = 12; // event: 32 B group, 4 B lookahead, group index, quarter reports, item (48 B)
 constexpr uint32_t UN_LUT_BYTES = 256 * 256; // 256-byte row per byte value; lanes use the first 128 B
 constexpr uint32_t FULL = 0xffffffffu;
 
 // Dynamic shared memory.  The LUT must start at a 64 KB-aligned shared address; the gap in front of it
 // (63 KB when the dynamic window starts at 0x400, the usual case) holds the event lists, the counters
-// and the verification tables; the per-warp row rings and their mbarriers follow
-// the LUT.
+// and the verification tables; the per-warp row rings follow the LUT.
 constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_WORDS * 4;
 constexpr uint32_t UN_RING_BYTES = UN_WARPS * UN_SLOTS * UN_SLOT_BYTES;
 constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
@@ -164,21 +171,6 @@ __device__ __forceinline__ uint32_t entry_window(uint32_t entry_sa, uint32_t pos
 }
 __device__ __forceinline__ uint32_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// 0x80 in every byte of w that is zero (exact, no false positives above a zero byte)
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t w)
-{
-    uint32_t t = (w & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-    return ~(t | w | 0x7f7f7f7fu);
-}
-__device__ __forceinline__ uint32_t pack4(uint32_t z) { return (((z >> 7) * 0x00204081u) >> 21) & 0xfu; }
-// bit i set when byte i of the 32-byte group is NUL
-__device__ __forceinline__ uint32_t zero_mask32(const uint32_t *w)
-{
-    uint32_t m = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) m |= pack4(zero_bytes(w[i])) << (4 * i);
-    return m;
-}
 // bits [lo, hi) of a 32-bit word, 0 <= lo, hi <= 32
 __device__ __forceinline__ uint32_t bit_window(uint32_t lo, uint32_t hi)
 {

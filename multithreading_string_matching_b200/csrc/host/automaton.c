@@ -138,21 +138,113 @@ static double split_buckets(const pat_ref *sorted, uint32_t n, uint32_t *cut)
     return total;
 }
 
+/* Buckets as multisets, so that patterns can be moved in and out: per depth, how many members have each
+ * byte value there, how many distinct values that makes, and how many members are too short to have one. */
+typedef struct {
+    uint16_t count[FILTER_DEPTH][256];
+    uint32_t distinct[FILTER_DEPTH], open[FILTER_DEPTH], members;
+} bucket_bag;
+
+static void bag_change(bucket_bag *g, const pat_ref *r, int add)
+{
+    for (uint32_t d = 0; d < FILTER_DEPTH; d++) {
+        if (d >= r->len) { g->open[d] += add ? 1 : -1; continue; }
+        uint16_t *c = &g->count[d][r->p[d]];
+        if (add) { if ((*c)++ == 0) g->distinct[d]++; }
+        else if (--(*c) == 0) g->distinct[d]--;
+    }
+    g->members += add ? 1 : -1;
+}
+
+static double bag_cost(const bucket_bag *g)
+{
+    if (g->members == 0) return 0.0;
+    double c = 1.0;
+    for (uint32_t d = 0; d < FILTER_DEPTH; d++) {
+        if (g->open[d]) continue;
+        double f = g->distinct[d] / TEXT_ALPHABET;
+        c *= f > 1.0 ? 1.0 : f;
+    }
+    return c;
+}
+
+#define REFINE_LIMIT 512 /* above this many distinct patterns the contiguous split is kept as it is */
+
+/* Hill climbing from the contiguous split: move single patterns, then swap pairs, while the summed
+ * candidate probability drops.  bucket[i] = bucket of sorted[i]. */
+static double refine_buckets(const pat_ref *sorted, uint32_t n, uint8_t *bucket)
+{
+    bucket_bag *bag = calloc(N_BUCKET, sizeof *bag);
+    if (!bag) return -1.0;
+    for (uint32_t i = 0; i < n; i++) bag_change(&bag[bucket[i]], &sorted[i], 1);
+    for (int sweep = 0, improved = 1; improved && sweep < 64; sweep++) {
+        improved = 0;
+        for (uint32_t i = 0; i < n; i++) { /* moves */
+            const uint32_t a = bucket[i];
+            const double ca = bag_cost(&bag[a]);
+            bag_change(&bag[a], &sorted[i], 0);
+            const double gain_out = ca - bag_cost(&bag[a]);
+            double best = -1e-15;
+            uint32_t to = a;
+            for (uint32_t b = 0; b < N_BUCKET; b++) {
+                if (b == a) continue;
+                const double cb = bag_cost(&bag[b]);
+                bag_change(&bag[b], &sorted[i], 1);
+                const double delta = bag_cost(&bag[b]) - cb - gain_out;
+                bag_change(&bag[b], &sorted[i], 0);
+                if (delta < best) { best = delta; to = b; }
+            }
+            bag_change(&bag[to], &sorted[i], 1);
+            if (to != a) { bucket[i] = (uint8_t)to; improved = 1; }
+        }
+        for (uint32_t i = 0; i < n; i++) /* swaps */
+            for (uint32_t j = i + 1; j < n; j++) {
+                const uint32_t a = bucket[i], b = bucket[j];
+                if (a == b) continue;
+                const double before = bag_cost(&bag[a]) + bag_cost(&bag[b]);
+                bag_change(&bag[a], &sorted[i], 0); bag_change(&bag[b], &sorted[j], 0);
+                bag_change(&bag[a], &sorted[j], 1); bag_change(&bag[b], &sorted[i], 1);
+                if (bag_cost(&bag[a]) + bag_cost(&bag[b]) < before - 1e-15) {
+                    bucket[i] = (uint8_t)b; bucket[j] = (uint8_t)a; improved = 1;
+                } else {
+                    bag_change(&bag[a], &sorted[j], 0); bag_change(&bag[b], &sorted[i], 0);
+                    bag_change(&bag[a], &sorted[i], 1); bag_change(&bag[b], &sorted[j], 1);
+                }
+            }
+    }
+    double total = 0;
+    for (uint32_t b = 0; b < N_BUCKET; b++) total += bag_cost(&bag[b]);
+    free(bag);
+    return total;
+}
+
 static void build_filter(kmpb_tables *t, pat_ref *uniq)
 {
     uint32_t cut[N_BUCKET + 1];
     qsort(uniq, t->n_uniq, sizeof *uniq, cmp_bucket);
     t->filter_fp_estimate = split_buckets(uniq, t->n_uniq, cut);
+    uint8_t *bucket = malloc(t->n_uniq ? t->n_uniq : 1);
     memset(t->filter, 0, sizeof t->filter);
+    if (bucket) {
+        for (uint32_t b = 0; b < N_BUCKET; b++)
+            for (uint32_t i = cut[b]; i < cut[b + 1]; i++) bucket[i] = (uint8_t)b;
+        if (t->n_uniq <= REFINE_LIMIT) {
+            double refined = refine_buckets(uniq, t->n_uniq, bucket);
+            if (refined >= 0) t->filter_fp_estimate = refined;
+        }
+    }
     for (uint32_t b = 0; b < N_BUCKET; b++) {
         bucket_sets s;
         memset(&s, 0, sizeof s);
-        if (cut[b] == cut[b + 1]) continue;
-        for (uint32_t i = cut[b]; i < cut[b + 1]; i++) sets_add(&s, &uniq[i]);
+        uint32_t members = 0;
+        for (uint32_t i = 0; i < t->n_uniq; i++)
+            if (bucket ? bucket[i] == b : (i >= cut[b] && i < cut[b + 1])) { sets_add(&s, &uniq[i]); members++; }
+        if (members == 0) continue;
         for (uint32_t c = 0; c < 256; c++)
             for (uint32_t d = 0; d < FILTER_DEPTH; d++)
                 if (s.open[d] || (s.set[d][c >> 6] >> (c & 63) & 1)) t->filter[c] |= 1u << (8 * d + b);
     }
+    free(bucket);
     /* bucket 7: stages 0..2 always pass, stage 3 passes on NUL only -> bit 31 of the running
      * shift-and word is set exactly on a NUL byte */
     for (uint32_t c = 0; c < 256; c++) t->filter[c] |= 0x00808080u;
