@@ -56,27 +56,69 @@ def measured_hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every few ms WHILE the timed region runs: NVML in a thread
+    (nvidia_ml_py), nvidia-smi -lms as the fallback."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.path = None
+        self.proc = self.path = self.thread = None
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self.stop_flag = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in visible.split(",") if v.strip().isdigit()]
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(ids[self.gpu]) if self.gpu < len(ids) else self.gpu)
+
+    def _loop(self, pynvml, h):
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                bits = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS:
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            pynvml, h = self._nvml_handle()
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, args=(pynvml, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         if shutil.which("nvidia-smi") is None:
             return
         fd, self.path = tempfile.mkstemp(suffix=".csv")
         os.close(fd)
         self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits", "-lms", "200"],
+                                      "--format=csv,noheader,nounits", "-lms", "20"],
                                      stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": None}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.sm_max, reasons=sorted(self.reasons),
+                           samples=len(self.samples), how="NVML in a thread during the timed steps")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -99,8 +141,21 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.path)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm),
+                       how="nvidia-smi -lms 20 during the timed steps")
         return out
+
+
+def measured_traffic(packets, payload_len):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
+    workload (profiles/r01_traffic.json), or None when the workload differs."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if int(t["packets"]) == int(packets) and int(t["payload_len"]) == int(payload_len):
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
 
 
 # ---- CPU reference arm ---------------------------------------------------------------------------
@@ -225,7 +280,9 @@ def reference_arm(args, kmp, patterns):
         "impl": "reference", "metric": "payload_GBps", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "synthetic UDP pcap, %d B payloads, bundled strings.txt (97 patterns)" % args.payload_len,
+        "config": {"workload": "synthetic UDP pcap, %d packets x %d B payloads per GPU, bundled strings.txt (97 patterns, 87 distinct)"
+                               % (args.packets, args.payload_len),
+                   "sample": "each step = the first %d packets of that stream on the host cores" % n,
                    "packets_per_step": n, "payload_bytes_per_step": payload},
         "packets_per_s": n / (ms / 1e3),
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": ref.cores, "kind": ref.kind, "sample": ref.sample_text()},
@@ -299,6 +356,7 @@ def ours(args, kmp, patterns):
         step()
     e1.record()
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = (m.launches - launches0) // max(args.steps, 1) + 1  # + the counter reset
     counts_resident = d_counts.cpu().numpy().copy()
@@ -310,7 +368,6 @@ def ours(args, kmp, patterns):
         step()
         kms.append(m.last_kernel_ms())
     m.set_profile(False)
-    clocks = sampler.stop() if rank == 0 else None
     kernel_ms = max_over_ranks(float(np.mean(kms)))
     algo_bytes = nbytes + 8 * (count + 1)  # payload once + one offset per packet
     peak, peak_src = measured_hbm_peak()
@@ -385,7 +442,7 @@ def ours(args, kmp, patterns):
             "packets_per_s": total_packets / (ms_step / 1e3),
             "hbm_frac_of_measured_peak": value / world / peak,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "kmpb_union_kernel" if args.engine != "perpat" else "kmpb_perpat_kernel",
+                         "traffic": measured_traffic(count, L) if args.engine != "perpat" else None, "kernel": "kmpb_union_kernel" if args.engine != "perpat" else "kmpb_perpat_kernel",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "matches_per_step": int(counts_resident.sum()),
@@ -413,7 +470,7 @@ def ours(args, kmp, patterns):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--packets", type=int, default=10_000_000, help="packets per GPU (BASELINE config 3: 10 M)")
