@@ -319,16 +319,38 @@ def ours(args, kmp, patterns):
     d_bytes[nbytes:].zero_()
     d_off = torch.empty(count + 1, dtype=torch.int64, device=dev)
     synth.fill_device(m, first, count, d_bytes.data_ptr(), d_off.data_ptr())
-    d_counts = torch.zeros(n_pat, dtype=torch.int64, device=dev)
+    # two count vectors: the all-reduce of step i runs on a side stream while step i+1's kernel matches the
+    # next batch (in a pipeline the batches differ; here it is the same slice again)
+    d_counts2 = [torch.zeros(n_pat, dtype=torch.int64, device=dev) for _ in range(2)]
+    d_counts = d_counts2[0]
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    reduced = [None, None]
+    step_no = [0]
 
     def step():
-        d_counts.zero_()
-        m.count_device(d_bytes.data_ptr(), d_off.data_ptr(), count, d_counts.data_ptr(), span=(0, nbytes),
+        i = step_no[0] & 1
+        step_no[0] += 1
+        buf = d_counts2[i]
+        if reduced[i] is not None:
+            stream.wait_event(reduced[i])  # the vector's previous all-reduce has read it
+        buf.zero_()
+        m.count_device(d_bytes.data_ptr(), d_off.data_ptr(), count, buf.data_ptr(), span=(0, nbytes),
                        stream=stream.cuda_stream)
         if world > 1:
-            kd.reduce_counts(d_counts)  # the MPI_Reduce(SUM) of mpi_dumping.c:202, as an NCCL all-reduce over NVLink
+            ready = torch.cuda.Event()
+            ready.record(stream)
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                kd.reduce_counts(buf)  # the MPI_Reduce(SUM) of mpi_dumping.c:202, as an NCCL all-reduce over NVLink
+                reduced[i] = torch.cuda.Event()
+                reduced[i].record(side)
+        return buf
+
+    def drain_side():
+        if world > 1:
+            stream.wait_stream(side)
 
     def barrier():
         if world > 1:
@@ -345,6 +367,7 @@ def ours(args, kmp, patterns):
     # ---- device-resident timing -------------------------------------------------------------------
     for _ in range(args.warmup):
         step()
+    drain_side()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -353,7 +376,8 @@ def ours(args, kmp, patterns):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step()
+        d_counts = step()
+    drain_side()  # the last all-reduce is inside the timed region
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -367,6 +391,7 @@ def ours(args, kmp, patterns):
     for _ in range(max(3, min(args.steps, 10))):
         step()
         kms.append(m.last_kernel_ms())
+    drain_side()
     m.set_profile(False)
     kernel_ms = max_over_ranks(float(np.mean(kms)))
     algo_bytes = nbytes + 8 * (count + 1)  # payload once + one offset per packet
@@ -437,7 +462,7 @@ def ours(args, kmp, patterns):
             "config": {"workload": "synthetic UDP pcap, %d packets x %d B payloads per GPU, bundled strings.txt (97 patterns, 87 distinct)"
                                    % (per_gpu, L),
                        "packets_total": total_packets, "payload_bytes_total": int(total_bytes), "engine": args.engine,
-                       "split": "mpi_dumping.c:149-157 contiguous packet slices, counts summed by NCCL all-reduce",
+                       "split": "mpi_dumping.c:149-157 contiguous packet slices, counts summed by one NCCL all-reduce per step (side stream, overlapped with the next step's kernel)",
                        "l2": "inputs (%.1f GB per GPU) larger than the 126 MB L2; no flush needed" % (nbytes / 1e9)},
             "packets_per_s": total_packets / (ms_step / 1e3),
             "hbm_frac_of_measured_peak": value / world / peak,
