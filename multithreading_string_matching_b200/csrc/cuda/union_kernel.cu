@@ -276,17 +276,19 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_s
                 bool same = true;
                 for (uint32_t j = 4; j < m && same; j += 4) { // pattern bytes j..j+3 against text bytes i+j..
                     const uint32_t pw = vt(pw0 + (j >> 2)), rem = m - j;
-                    if (i + j + 4 <= 36) {
-                        const uint32_t diff = entry_window(entry_sa, i + j) ^ pw;
-                        same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
-                    } else { // past the bytes carried along: byte by byte, event first, then global memory
-                        const uint8_t *gb = c.bytes + (uint64_t)UN_GRP * lds32v(entry_sa + 36);
-                        for (uint32_t b = 0; b < 4 && b < rem && same; b++) {
-                            const uint32_t pos = i + j + b;
-                            const uint32_t t = pos < 36 ? lds8v(entry_sa + pos) : (uint32_t)gb[pos];
-                            same = t == ((pw >> (8 * b)) & 0xffu);
-                        }
+                    // text bytes i+j..: from the event while they last (36 bytes), then from global memory
+                    const uint32_t pos = i + j;
+                    uint32_t t4;
+                    if (pos + 4 <= 36) {
+                        t4 = entry_window(entry_sa, pos);
+                    } else {
+                        const uint8_t *gw = c.bytes + (uint64_t)UN_GRP * lds32v(entry_sa + 36) + (pos & ~3u);
+                        const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(gw));
+                        const uint32_t hi = (pos & 3u) + (rem < 4 ? rem : 4u) > 4u ? __ldg(reinterpret_cast<const uint32_t *>(gw) + 1) : 0u;
+                        t4 = __funnelshift_r(lo, hi, 8u * (pos & 3u));
                     }
+                    const uint32_t diff = t4 ^ pw;
+                    same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
                 }
                 if (same) count_hit(c, u);
             }
@@ -355,9 +357,23 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
     uint32_t am = 0, bm = 0, nextb = 255; // alive candidates; packet starts inside the group (bit = offset);
                                           // offset of the first packet start at or after the group's end
     if (cm) {
-        // the packet that holds my first candidate: the last k in [ks, ke) with offsets[k] <= p0
+        // The packet that holds my first candidate: the last k in [ks, ke) with offsets[k] <= p0.  First
+        // guess by interpolation (exact for equal-sized packets), then a binary search in what is left.
         const uint64_t p0 = gq + (__ffs(cm) - 1);
         uint32_t k = ks, k1 = ke;
+        {
+            const float frac = (float)(uint32_t)(p0 - b_abs) / (float)(uint32_t)(e_abs - b_abs);
+            uint32_t kg = ks + (uint32_t)(frac * (float)(ke - ks));
+            kg = kg >= ke ? ke - 1 : kg;
+            const uint64_t o0 = __ldg(c.offsets + kg), o1 = __ldg(c.offsets + kg + 1);
+            if (o0 <= p0) {
+                k = kg;
+                if (p0 < o1) k1 = kg + 1;
+                else k = kg + 1; // offsets[kg + 1] <= p0 < e_abs, so kg + 1 < ke
+            } else {
+                k1 = kg;
+            }
+        }
         while (k1 - k > 1) {
             const uint32_t mid = k + (k1 - k) / 2;
             if (__ldg(c.offsets + mid) <= p0) k = mid; else k1 = mid;
