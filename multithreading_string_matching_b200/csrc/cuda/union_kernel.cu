@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         const uint32_t e_rel = (uint32_t)(e_abs - row0);
         const uint32_t load_end = (e_rel + 15u) & ~15u;
         const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
-        uint32_t g32 = (uint32_t)((row0 - p.abs_base) >> 5) + lane; // my group's index in 32-byte units
+        const uint32_t g32 = (uint32_t)((row0 - p.abs_base) >> 5) + lane; // my group's index in row 0, in 32-byte units
 
         // Every lane copies its own 32 bytes (lane 0 also the 16 bytes after the row) with 16-byte
         // asynchronous copies.  One commit group per call, also when there is nothing left to copy, so
@@ -549,9 +549,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         };
         for (uint32_t r = 0; r < UN_SLOTS; r++) issue_row(r, r);
 
-        uint32_t slot = 0;
-#pragma unroll 1
-        for (uint32_t r = 0; r < nrows; r++, g32 += 32) {
+        // one row: wait for its slot, filter, refill the slot, push the events
+        auto scan_row = [&](const uint32_t r, const uint32_t slot) {
             cp_async_wait<UN_SLOTS - 1>();
             __syncwarp(); // my lookahead is the next lane's copy
             const uint32_t base = ring_sa + slot * UN_SLOT_BYTES;
@@ -599,7 +598,6 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
 
             // every lane holds its bytes: refill the slot with the row UN_SLOTS ahead
             issue_row(r + UN_SLOTS, slot);
-            slot = slot + 1 == UN_SLOTS ? 0 : slot + 1;
 
 #ifdef KMPB_ABLATE_SLOW_PATH // measurement only (wrong counts): how fast is the fast path alone?
             if (m == 0x12345678u)
@@ -614,11 +612,26 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                     const uint32_t e = q_sa + (qn + __popc(m & lt)) * (UN_Q_WORDS * 4);
                     sts128v(e, c0.x, c0.y, c0.z, c0.w);
                     sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
-                    sts128v(e + 32, la, g32, tops, item);
+                    sts128v(e + 32, la, g32 + (r << 5), tops, item);
                 }
                 qn += n;
             }
+        };
+#if KMPB_UN_SLOTS == 2
+        // two rows per trip: the slots are compile-time constants, half the loop bookkeeping
+#pragma unroll 1
+        for (uint32_t r = 0; r < nrows; r += 2) {
+            scan_row(r, 0);
+            if (r + 1 < nrows) scan_row(r + 1, 1);
         }
+#else
+        uint32_t slot = 0;
+#pragma unroll 1
+        for (uint32_t r = 0; r < nrows; r++) {
+            scan_row(r, slot);
+            slot = slot + 1 == UN_SLOTS ? 0 : slot + 1;
+        }
+#endif
     }
     // leftovers
     if (qn) carry = drain_events(sc, q_sa, qn, carry, lutlane, mul);
