@@ -485,6 +485,14 @@ def ours(args, kmp, patterns):
             ours_text = kmp.format_report(patterns, d_c.cpu().tolist()).decode("latin-1")
             line["cpu_baseline"] = {"value": n * L / secs / 1e9, "unit": "GB/s", "cores": ref.cores, "kind": ref.kind,
                                     "sample": ref.sample_text(), "seconds": secs, "counts_match_gpu": ours_text == text}
+            if ref.kind == "reference":
+                # the step before the path: savefile -> pinned CSR batch, on the same sample pcap
+                t0 = time.perf_counter()
+                batch = kmp.PayloadBatch(ref.pcap, "udp", pinned=True)
+                dt = time.perf_counter() - t0
+                line["ingest"] = {"value": batch.total_bytes / dt / 1e9, "unit": "GB/s", "seconds": dt, "packets": int(batch.n_packets),
+                                  "what": "kmpb_load_pcap_csr (mmap, sequential record framing, OpenMP pack into pinned memory) on the CPU sample's pcap"}
+                batch.close()
             ref.close()
         print(json.dumps(line), flush=True)
     m.close()

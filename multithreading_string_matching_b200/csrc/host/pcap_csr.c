@@ -2,9 +2,11 @@
  *
  * The reference lets libpcap frame the records (pcap_open_offline serial.c:91, pcap_next_ex :115),
  * copies every frame, extracts its payload and stores one malloc'd buffer per payload.  Here the
- * savefile is mapped, walked twice (size, then copy) and the accepted payloads are packed back to
- * back into ONE flat buffer plus an offsets array -- the CSR batch the device consumes -- in pinned
- * memory so the H2D copies can run asynchronously.
+ * savefile is mapped, the records are framed and their payloads located in one sequential pass, and
+ * the accepted payloads are then packed back to back by all host threads (OpenMP, like the
+ * reference's own extraction loop at openmp_data.c:128-147) into ONE flat buffer plus an offsets
+ * array -- the CSR batch the device consumes -- in pinned memory so the H2D copies can run
+ * asynchronously.
  *
  * Frames are read with their captured length (openmp_data.c:114-116; serial.c:117-120 uses the wire
  * length, the same number whenever caplen == len).  Like the reference's `while (pcap_next_ex(...)
@@ -33,12 +35,21 @@ static uint32_t load32(const uint8_t *p, int swapped)
     return swapped ? __builtin_bswap32(v) : v;
 }
 
-/* One pass over the records.  With dst == NULL it only sizes the batch. */
-static void walk(const uint8_t *file, size_t size, int swapped, extract_fn extract,
-                 uint8_t *dst, uint64_t *offsets, uint64_t *n_packets, uint64_t *n_frames, uint64_t *total)
+/* Where an accepted payload lies in the mapped file. */
+typedef struct {
+    uint64_t at;  /* file offset of the payload's first byte */
+    uint32_t len;
+} payload_ref;
+
+/* Pass 1, sequential (record n+1 starts where record n's header says): frame the records, run the
+ * extractor on every frame and remember where the accepted payloads are. */
+static int index_records(const uint8_t *file, size_t size, int swapped, extract_fn extract, payload_ref **refs_out,
+                         uint64_t *n_packets, uint64_t *n_frames, uint64_t *total)
 {
-    size_t at = PCAP_GLOBAL_HDR;
+    size_t at = PCAP_GLOBAL_HDR, cap = 1u << 16;
     uint64_t packets = 0, frames = 0, bytes = 0;
+    payload_ref *refs = malloc(cap * sizeof *refs);
+    if (!refs) return KMPB_ENOMEM;
     while (size - at >= PCAP_RECORD_HDR) {
         uint32_t caplen = load32(file + at + 8, swapped);
         at += PCAP_RECORD_HDR;
@@ -46,19 +57,62 @@ static void walk(const uint8_t *file, size_t size, int swapped, extract_fn extra
         uint32_t off, len;
         frames++;
         if (extract(file + at, caplen, &off, &len)) {
-            if (dst) {
-                memcpy(dst + bytes, file + at + off, len);
-                offsets[packets] = bytes;
+            if (packets == cap) {
+                payload_ref *grown = realloc(refs, 2 * cap * sizeof *refs);
+                if (!grown) { free(refs); return KMPB_ENOMEM; }
+                refs = grown;
+                cap *= 2;
             }
+            refs[packets].at = at + off;
+            refs[packets].len = len;
             bytes += len;
             packets++;
         }
         at += caplen;
     }
-    if (dst) offsets[packets] = bytes;
+    *refs_out = refs;
     *n_packets = packets;
     *n_frames = frames;
     *total = bytes;
+    return KMPB_OK;
+}
+
+/* Pass 2, parallel: offsets by a two-level prefix sum, payloads copied by all host threads (the copy
+ * is what the reference does per packet at serial.c:124-137, here into one flat buffer). */
+static void pack_payloads(const uint8_t *file, const payload_ref *refs, uint64_t n, uint8_t *dst, uint64_t *offsets)
+{
+    enum { BLOCK = 4096 };
+    const uint64_t n_blocks = (n + BLOCK - 1) / BLOCK;
+    uint64_t *block_base = malloc((size_t)(n_blocks + 1) * sizeof *block_base);
+    if (block_base == NULL) { /* no scratch: plain sequential pack */
+        uint64_t bytes = 0;
+        for (uint64_t k = 0; k < n; k++) {
+            offsets[k] = bytes;
+            memcpy(dst + bytes, file + refs[k].at, refs[k].len);
+            bytes += refs[k].len;
+        }
+        offsets[n] = bytes;
+        return;
+    }
+#pragma omp parallel for schedule(static)
+    for (uint64_t b = 0; b < n_blocks; b++) {
+        uint64_t sum = 0, hi = (b + 1) * BLOCK < n ? (b + 1) * BLOCK : n;
+        for (uint64_t k = b * BLOCK; k < hi; k++) sum += refs[k].len;
+        block_base[b + 1] = sum;
+    }
+    block_base[0] = 0;
+    for (uint64_t b = 0; b < n_blocks; b++) block_base[b + 1] += block_base[b];
+#pragma omp parallel for schedule(dynamic, 4)
+    for (uint64_t b = 0; b < n_blocks; b++) {
+        uint64_t bytes = block_base[b], hi = (b + 1) * BLOCK < n ? (b + 1) * BLOCK : n;
+        for (uint64_t k = b * BLOCK; k < hi; k++) {
+            offsets[k] = bytes;
+            memcpy(dst + bytes, file + refs[k].at, refs[k].len);
+            bytes += refs[k].len;
+        }
+    }
+    offsets[n] = block_base[n_blocks];
+    free(block_base);
 }
 
 int kmpb_load_pcap_csr(const char *path, int proto, int pinned, kmpb_csr *out)
@@ -84,7 +138,7 @@ int kmpb_load_pcap_csr(const char *path, int proto, int pinned, kmpb_csr *out)
     const uint8_t *file = mmap(NULL, size, PROT_READ, MAP_PRIVATE, fd, 0);
     close(fd);
     if (file == MAP_FAILED) return kmpb_fail(KMPB_EIO, "%s: mmap: %s", path, strerror(errno));
-    madvise((void *)file, size, MADV_SEQUENTIAL);
+    madvise((void *)file, size, MADV_WILLNEED);
 
     uint32_t magic;
     memcpy(&magic, file, 4);
@@ -98,7 +152,11 @@ int kmpb_load_pcap_csr(const char *path, int proto, int pinned, kmpb_csr *out)
     extract_fn extract = proto == KMPB_PROTO_TCP ? kmpb_extract_tcp : kmpb_extract_udp;
 
     uint64_t n = 0, frames = 0, total = 0;
-    walk(file, size, swapped, extract, NULL, NULL, &n, &frames, &total);
+    payload_ref *refs = NULL;
+    if (index_records(file, size, swapped, extract, &refs, &n, &frames, &total) != KMPB_OK) {
+        munmap((void *)file, size);
+        return kmpb_fail(KMPB_ENOMEM, "out of memory indexing %s", path);
+    }
 
     size_t bytes_sz = (size_t)total + CSR_TAIL_PAD, off_sz = (size_t)(n + 1) * sizeof(uint64_t);
     uint8_t *bytes = pinned ? kmpb_host_alloc(bytes_sz) : malloc(bytes_sz);
@@ -107,10 +165,12 @@ int kmpb_load_pcap_csr(const char *path, int proto, int pinned, kmpb_csr *out)
         if (pinned) { kmpb_host_free(bytes); kmpb_host_free(offsets); }
         else { free(bytes); free(offsets); }
         munmap((void *)file, size);
+        free(refs);
         return kmpb_fail(KMPB_ENOMEM, "cannot allocate %zu bytes of %s memory for the payload batch",
                          bytes_sz + off_sz, pinned ? "pinned" : "host");
     }
-    walk(file, size, swapped, extract, bytes, offsets, &n, &frames, &total);
+    pack_payloads(file, refs, n, bytes, offsets);
+    free(refs);
     memset(bytes + total, 0, CSR_TAIL_PAD);
     munmap((void *)file, size);
 
