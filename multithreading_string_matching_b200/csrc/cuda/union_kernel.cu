@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     // Inside a slot lane l owns bytes [32 l, 32 l + 32); lanes 4..7, 12..15, ... keep their two 16-byte
     // halves swapped, which makes the 16-byte copies and reads of a quarter-warp hit 8 different bank groups.
     const uint32_t ring_sa = saddr_of(ring_all) + warp * (UN_SLOTS * UN_SLOT_BYTES);
+    const uint32_t offtail = UN_ROW;
 #ifdef KMPB_UN_NOSWIZZLE
     const uint32_t off0 = lane * UN_GRP, off1 = off0 + 16, offla = off0 + UN_GRP;
 #else
@@ -528,8 +529,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
         const uint32_t g32 = (uint32_t)((row0 - p.abs_base) >> 5) + lane; // my group's index in row 0, in 32-byte units
 
-        // Every lane copies its own 32 bytes (lane 0 also the 16 bytes after the row) with 16-byte
-        // asynchronous copies.  One commit group per call, also when there is nothing left to copy, so
+        // Every lane copies its own 32 bytes (lane 31 also the 16 bytes after the row -- they follow its own
+        // -- into the slot's tail) with 16-byte asynchronous copies.  One commit group per call, also when there is nothing left to copy, so
         // that "all but the newest UN_SLOTS-1 groups are complete" always means "the row about to be
         // scanned has arrived".  (A chunk-major slot layout, free of bank conflicts on both sides, measured
         // 14 % slower on the fast path alone.)
@@ -539,11 +540,11 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             if (row + UN_SLOT_BYTES <= load_end) {
                 cp_async16(dst + off0, text + g);
                 cp_async16(dst + off1, text + g + 16);
-                if (lane == 0) cp_async16(dst + UN_ROW, text + row + UN_ROW);
+                if (lane == 31) cp_async16(dst + offtail, text + g + 32);
             } else if (r < nrows) {
                 if (g < load_end) cp_async16(dst + off0, text + g);
                 if (g + 16 < load_end) cp_async16(dst + off1, text + g + 16);
-                if (lane == 0 && row + UN_ROW < load_end) cp_async16(dst + UN_ROW, text + row + UN_ROW);
+                if (lane == 31 && g + 32 < load_end) cp_async16(dst + offtail, text + g + 32);
             }
             cp_async_commit();
         };
