@@ -171,6 +171,21 @@ typedef struct kmpb_csr {
 int kmpb_load_pcap_csr(const char *path, int proto, int pinned, kmpb_csr *out);
 void kmpb_free_csr(kmpb_csr *csr);
 
+/* The same ingest loop fused with the match loop, serial.c:91-155 (the producer/consumer shape of
+ * openmp_task.c:113-178: batches of packets are matched while the next batch is being read).
+ * kmpb_pcap_open maps the savefile, frames its records and locates the accepted payloads (one
+ * sequential pass, nothing copied).  kmpb_count_pcap counts the patterns in accepted packets
+ * [first, first+count) -- a rank's slice as kmpb_shard_range gives it, or everything -- by packing
+ * ~64 MiB batches of payloads into pinned staging buffers (all host threads), copying each to the
+ * device and matching it while the next one is packed.  counts_out[n_pat] is caller-owned. */
+typedef struct kmpb_pcap kmpb_pcap;
+int kmpb_pcap_open(const char *path, int proto, kmpb_pcap **out);
+void kmpb_pcap_close(kmpb_pcap *pc);
+uint64_t kmpb_pcap_packets(const kmpb_pcap *pc); /* frames whose payload the extractor accepted */
+uint64_t kmpb_pcap_frames(const kmpb_pcap *pc);  /* records in the file */
+uint64_t kmpb_pcap_bytes(const kmpb_pcap *pc);   /* sum of the accepted payload lengths */
+int kmpb_count_pcap(kmpb_ctx *ctx, const kmpb_pcap *pc, uint64_t first, uint64_t count, uint64_t *counts_out);
+
 /* The report, serial.c:163-168: header line, then "pattern: N times!" for every pattern with a
  * non-zero count, in pattern order.  Writes to `stream` (a FILE*, passed as void*). */
 int kmpb_print_report(void *stream, const kmpb_patterns *pats, const uint64_t *counts);

@@ -65,6 +65,12 @@ SIGNATURES = {
     "kmpb_free_patterns": (None, [ctypes.POINTER(CPatterns)]),
     "kmpb_load_pcap_csr": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(CCsr)]),
     "kmpb_free_csr": (None, [ctypes.POINTER(CCsr)]),
+    "kmpb_pcap_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "kmpb_pcap_close": (None, [ctypes.c_void_p]),
+    "kmpb_pcap_packets": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "kmpb_pcap_frames": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "kmpb_pcap_bytes": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "kmpb_count_pcap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, c_u64p]),
     "kmpb_print_report": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CPatterns), c_u64p]),
     "kmpb_synth_bytes": (ctypes.c_uint64, [ctypes.POINTER(CSynth), ctypes.c_uint64, ctypes.c_uint64]),
     "kmpb_synth_fill_host": (ctypes.c_int, [ctypes.POINTER(CSynth), ctypes.c_uint64, ctypes.c_uint64,

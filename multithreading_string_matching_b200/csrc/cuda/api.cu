@@ -1,8 +1,10 @@
 // api.cu -- the C ABI of include/kmpb200.h: context, pattern upload, the two count entry points.
 #include <algorithm>
 #include <new>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <vector>
 
 #include "kmpb_device.cuh"
@@ -40,6 +42,82 @@ int run_engine(kmpb_ctx *ctx, const kmpb_batch &b, int slot, cudaStream_t stream
     uint64_t *acc = ctx->d_uniq_counts + (size_t)slot * ctx->host.n_uniq;
     if (ctx->engine == KMPB_ENGINE_PERPAT) return kmpb_launch_perpat(ctx, b, acc, stream);
     return kmpb_launch_union(ctx, b, slot, acc, stream);
+}
+
+// device staging slots for chunked host input (grown on demand, kept for the next call)
+int ensure_staging(kmpb_ctx *ctx, uint64_t max_bytes, uint64_t max_pkts)
+{
+    if (max_bytes + 1024 <= ctx->stage_bytes_cap && max_pkts + 1 <= ctx->stage_off_cap) return KMPB_OK;
+    KMPB_CUDA(cudaDeviceSynchronize());
+    const size_t bcap = std::max<size_t>(ctx->stage_bytes_cap, (size_t)max_bytes + 1024);
+    const size_t ocap = std::max<size_t>(ctx->stage_off_cap, (size_t)max_pkts + 1);
+    for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
+        cudaFree(ctx->d_stage_bytes[i]); ctx->d_stage_bytes[i] = nullptr;
+        cudaFree(ctx->d_stage_off[i]); ctx->d_stage_off[i] = nullptr;
+    }
+    ctx->stage_bytes_cap = ctx->stage_off_cap = 0;
+    for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
+        KMPB_CUDA(cudaMalloc((void **)&ctx->d_stage_bytes[i], bcap));
+        KMPB_CUDA(cudaMemset(ctx->d_stage_bytes[i], 0, bcap));
+        KMPB_CUDA(cudaMalloc((void **)&ctx->d_stage_off[i], ocap * sizeof(uint64_t)));
+    }
+    ctx->stage_bytes_cap = bcap;
+    ctx->stage_off_cap = ocap;
+    return KMPB_OK;
+}
+
+// ... and their pinned twins on the host
+int ensure_host_staging(kmpb_ctx *ctx, uint64_t max_bytes, uint64_t max_pkts)
+{
+    if (max_bytes + 1024 <= ctx->h_stage_bytes_cap && max_pkts + 1 <= ctx->h_stage_off_cap) return KMPB_OK;
+    KMPB_CUDA(cudaDeviceSynchronize());
+    const size_t bcap = std::max<size_t>(ctx->h_stage_bytes_cap, (size_t)max_bytes + 1024);
+    const size_t ocap = std::max<size_t>(ctx->h_stage_off_cap, (size_t)max_pkts + 1);
+    for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
+        cudaFreeHost(ctx->h_stage_bytes[i]); ctx->h_stage_bytes[i] = nullptr;
+        cudaFreeHost(ctx->h_stage_off[i]); ctx->h_stage_off[i] = nullptr;
+    }
+    ctx->h_stage_bytes_cap = ctx->h_stage_off_cap = 0;
+    for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
+        KMPB_CUDA(cudaHostAlloc((void **)&ctx->h_stage_bytes[i], bcap, cudaHostAllocDefault));
+        KMPB_CUDA(cudaHostAlloc((void **)&ctx->h_stage_off[i], ocap * sizeof(uint64_t), cudaHostAllocDefault));
+        if (!ctx->ev_h2d[i]) KMPB_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+    }
+    ctx->h_stage_bytes_cap = bcap;
+    ctx->h_stage_off_cap = ocap;
+    return KMPB_OK;
+}
+
+// sums the per-slot accumulators into file order, copies them out and reports device-side error flags
+int finish_chunked(kmpb_ctx *ctx, int n_slots, uint64_t *counts_out)
+{
+    const uint32_t n_pat = ctx->host.n_pat, nu = ctx->host.n_uniq;
+    for (int s = 0; s < n_slots; s++) {
+        KMPB_CUDA(cudaEventRecord(ctx->ev[3], ctx->copy_stream[s]));
+        KMPB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev[3], 0));
+    }
+    kmpb_expand_counts_kernel<<<(n_pat + 255) / 256, 256, 0, ctx->stream>>>(
+        (const unsigned long long *)ctx->d_uniq_counts, nu, KMPB_COPY_STREAMS, ctx->dev.pat_to_uniq, n_pat,
+        (unsigned long long *)ctx->d_counts, 0);
+    ctx->launches++;
+    KMPB_CUDA(cudaGetLastError());
+    KMPB_CUDA(cudaMemcpyAsync(counts_out, ctx->d_counts, (size_t)n_pat * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KMPB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    KMPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    KMPB_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->last_ms[0] = ms;
+    ctx->last_ms[1] = 0;
+    // device-side error flags of the union engine (oversized packets)
+    if (ctx->engine != KMPB_ENGINE_PERPAT && ctx->d_work) {
+        uint32_t work[KMPB_COPY_STREAMS * 4];
+        KMPB_CUDA(cudaMemcpy(work, ctx->d_work, sizeof work, cudaMemcpyDeviceToHost));
+        for (int s = 0; s < n_slots; s++)
+            if (work[s * 4 + 1])
+                return kmpb_fail(KMPB_ELIMIT, work[s * 4 + 1] & 2u ? "unexpected shared-memory window layout on this device"
+                                                                   : "a packet of 2 GiB or more is not supported");
+    }
+    return KMPB_OK;
 }
 
 } // namespace
@@ -96,6 +174,9 @@ void kmpb_destroy(kmpb_ctx *ctx)
     for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
         cudaFree(ctx->d_stage_bytes[i]);
         cudaFree(ctx->d_stage_off[i]);
+        cudaFreeHost(ctx->h_stage_bytes[i]);
+        cudaFreeHost(ctx->h_stage_off[i]);
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
     }
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -257,24 +338,7 @@ int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets
         k0 = k1;
     }
     const int n_slots = (int)std::min<size_t>(KMPB_COPY_STREAMS, plan.size());
-    // staging (grown on demand, kept for the next call)
-    if (max_bytes + 1024 > ctx->stage_bytes_cap || max_pkts + 1 > ctx->stage_off_cap) {
-        KMPB_CUDA(cudaDeviceSynchronize());
-        const size_t bcap = std::max<size_t>(ctx->stage_bytes_cap, (size_t)max_bytes + 1024);
-        const size_t ocap = std::max<size_t>(ctx->stage_off_cap, (size_t)max_pkts + 1);
-        for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
-            cudaFree(ctx->d_stage_bytes[i]); ctx->d_stage_bytes[i] = nullptr;
-            cudaFree(ctx->d_stage_off[i]); ctx->d_stage_off[i] = nullptr;
-        }
-        ctx->stage_bytes_cap = ctx->stage_off_cap = 0;
-        for (int i = 0; i < KMPB_COPY_STREAMS; i++) {
-            KMPB_CUDA(cudaMalloc((void **)&ctx->d_stage_bytes[i], bcap));
-            KMPB_CUDA(cudaMemset(ctx->d_stage_bytes[i], 0, bcap));
-            KMPB_CUDA(cudaMalloc((void **)&ctx->d_stage_off[i], ocap * sizeof(uint64_t)));
-        }
-        ctx->stage_bytes_cap = bcap;
-        ctx->stage_off_cap = ocap;
-    }
+    if ((rc = ensure_staging(ctx, max_bytes, max_pkts))) return rc;
     if ((rc = kmpb_union_scratch(ctx, max_bytes))) return rc;
 
     KMPB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -291,32 +355,78 @@ int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets
         kmpb_batch b{ctx->d_stage_bytes[slot], base, ctx->d_stage_off[slot], k1 - k0, offsets[k0], offsets[k1]};
         if ((rc = run_engine(ctx, b, slot, s))) return rc;
     }
-    for (int s = 0; s < n_slots; s++) {
-        KMPB_CUDA(cudaEventRecord(ctx->ev[3], ctx->copy_stream[s]));
-        KMPB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev[3], 0));
+    return finish_chunked(ctx, n_slots, counts_out);
+}
+
+// Streamed savefile path: pack a chunk of payloads into a pinned staging slot (all host threads), copy
+// it to the slot's device twin and match it on the slot's stream while the next chunk is packed -- the
+// producer/consumer shape of openmp_task.c:113-178 with the GPU as the consumer.
+int kmpb_count_pcap(kmpb_ctx *ctx, const kmpb_pcap *pc, uint64_t first, uint64_t count, uint64_t *counts_out)
+{
+    if (ctx == nullptr || pc == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL argument");
+    if (!ctx->have_tables) return kmpb_fail(KMPB_ESTATE, "count before kmpb_set_patterns");
+    const uint32_t n_pat = ctx->host.n_pat, nu = ctx->host.n_uniq;
+    if (n_pat == 0) return KMPB_OK;
+    if (counts_out == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL counts_out");
+    memset(counts_out, 0, (size_t)n_pat * sizeof(uint64_t));
+    const uint64_t total = kmpb_pcap_packets(pc);
+    if (first > total || count > total - first) return kmpb_fail(KMPB_EINVAL, "packet range outside the file");
+    if (count == 0) return KMPB_OK;
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    uint64_t chunk_bytes = 64ull << 20;
+    if (const char *env = getenv("KMPB_CHUNK_MB")) {
+        long mb = atol(env);
+        if (mb > 0) chunk_bytes = (uint64_t)mb << 20;
     }
-    kmpb_expand_counts_kernel<<<(n_pat + 255) / 256, 256, 0, ctx->stream>>>(
-        (const unsigned long long *)ctx->d_uniq_counts, nu, KMPB_COPY_STREAMS, ctx->dev.pat_to_uniq, n_pat,
-        (unsigned long long *)ctx->d_counts, 0);
-    ctx->launches++;
-    KMPB_CUDA(cudaGetLastError());
-    KMPB_CUDA(cudaMemcpyAsync(counts_out, ctx->d_counts, (size_t)n_pat * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    KMPB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-    KMPB_CUDA(cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    KMPB_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-    ctx->last_ms[0] = ms;
-    ctx->last_ms[1] = 0;
-    // device-side error flags of the union engine (oversized packets)
-    if (ctx->engine != KMPB_ENGINE_PERPAT && ctx->d_work) {
-        uint32_t work[KMPB_COPY_STREAMS * 4];
-        KMPB_CUDA(cudaMemcpy(work, ctx->d_work, sizeof work, cudaMemcpyDeviceToHost));
-        for (int s = 0; s < n_slots; s++)
-            if (work[s * 4 + 1])
-                return kmpb_fail(KMPB_ELIMIT, work[s * 4 + 1] & 2u ? "unexpected shared-memory window layout on this device"
-                                                                   : "a packet of 2 GiB or more is not supported");
+    const uint64_t max_pkts = 1ull << 22, last = first + count;
+    // a packet larger than a chunk still travels whole: size the slots for the largest chunk of the plan
+    uint64_t max_bytes = 0, max_n = 0, n_chunks = 0;
+    for (uint64_t k0 = first; k0 < last; n_chunks++) {
+        uint64_t b = 0;
+        const uint64_t k1 = kmpb_pcap_chunk_end(pc, k0, last, chunk_bytes, max_pkts, &b);
+        max_bytes = std::max(max_bytes, b);
+        max_n = std::max(max_n, k1 - k0);
+        k0 = k1;
     }
-    return KMPB_OK;
+    if ((rc = ensure_staging(ctx, max_bytes, max_n))) return rc;
+    if ((rc = ensure_host_staging(ctx, max_bytes, max_n))) return rc;
+    if ((rc = kmpb_union_scratch(ctx, max_bytes))) return rc;
+    const int n_slots = (int)std::min<uint64_t>(KMPB_COPY_STREAMS, n_chunks);
+
+    KMPB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    KMPB_CUDA(cudaMemsetAsync(ctx->d_uniq_counts, 0, (size_t)KMPB_COPY_STREAMS * nu * sizeof(uint64_t), ctx->stream));
+    KMPB_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    for (int s = 0; s < n_slots; s++) KMPB_CUDA(cudaStreamWaitEvent(ctx->copy_stream[s], ctx->ev[2], 0));
+    uint64_t c = 0;
+    double t_wait = 0, t_pack = 0, t_issue = 0;
+    const bool stats = getenv("KMPB_STATS") != nullptr;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    for (uint64_t k0 = first; k0 < last; c++) {
+        const int slot = (int)(c % KMPB_COPY_STREAMS);
+        cudaStream_t s = ctx->copy_stream[slot];
+        uint64_t nbytes = 0;
+        const uint64_t k1 = kmpb_pcap_chunk_end(pc, k0, last, chunk_bytes, max_pkts, &nbytes);
+        const double t0 = now();
+        if (c >= KMPB_COPY_STREAMS) KMPB_CUDA(cudaEventSynchronize(ctx->ev_h2d[slot])); // the slot's last copy has left it
+        const double t1 = now();
+        kmpb_pcap_pack(pc, k0, k1 - k0, ctx->h_stage_bytes[slot], ctx->h_stage_off[slot]);
+        memset(ctx->h_stage_bytes[slot] + nbytes, 0, 64);
+        const double t2 = now();
+        KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_bytes[slot], ctx->h_stage_bytes[slot], nbytes + 64, cudaMemcpyHostToDevice, s));
+        KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_off[slot], ctx->h_stage_off[slot], (k1 - k0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        KMPB_CUDA(cudaEventRecord(ctx->ev_h2d[slot], s));
+        kmpb_batch b{ctx->d_stage_bytes[slot], 0, ctx->d_stage_off[slot], k1 - k0, 0, nbytes};
+        if ((rc = run_engine(ctx, b, slot, s))) return rc;
+        k0 = k1;
+        t_wait += t1 - t0;
+        t_pack += t2 - t1;
+        t_issue += now() - t2;
+    }
+    if (stats)
+        fprintf(stderr, "kmpb_count_pcap: %llu chunks; waiting for a free slot %.3f s, packing %.3f s, issuing copies and kernels %.3f s\n",
+                (unsigned long long)c, t_wait, t_pack, t_issue);
+    return finish_chunked(ctx, n_slots, counts_out);
 }
 
 void *kmpb_host_alloc(size_t bytes)

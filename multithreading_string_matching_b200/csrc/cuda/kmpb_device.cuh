@@ -60,6 +60,11 @@ struct kmpb_ctx {
     uint8_t *d_stage_bytes[KMPB_COPY_STREAMS] = {};
     uint64_t *d_stage_off[KMPB_COPY_STREAMS] = {};
     size_t stage_bytes_cap = 0, stage_off_cap = 0;
+    // pinned twins of the staging slots for the streamed savefile path (kmpb_count_pcap)
+    uint8_t *h_stage_bytes[KMPB_COPY_STREAMS] = {};
+    uint64_t *h_stage_off[KMPB_COPY_STREAMS] = {};
+    size_t h_stage_bytes_cap = 0, h_stage_off_cap = 0;
+    cudaEvent_t ev_h2d[KMPB_COPY_STREAMS] = {};
     uint64_t *d_counts = nullptr;        // [n_pat] result of kmpb_count_host
     bool attr_union_set = false, attr_perpat_set = false; // per-device function attributes
     uint64_t launches = 0;

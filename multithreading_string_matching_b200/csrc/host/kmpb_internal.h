@@ -66,6 +66,13 @@ typedef struct kmpb_tables {
     double filter_fp_estimate;     /* estimated candidate probability per text byte, uniform bytes */
 } kmpb_tables;
 
+/* pcap_csr.c, used by the streamed savefile path (api.cu): end of the chunk of whole packets that starts at
+ * `first`, holds at most max_bytes payload bytes (at least one packet) and max_packets packets and stops
+ * before `last`; packs packets [first, first+count) back to back into dst, offsets[0..count] from 0 */
+uint64_t kmpb_pcap_chunk_end(const kmpb_pcap *pc, uint64_t first, uint64_t last, uint64_t max_bytes, uint64_t max_packets,
+                             uint64_t *bytes_out);
+void kmpb_pcap_pack(const kmpb_pcap *pc, uint64_t first, uint64_t count, uint8_t *dst, uint64_t *offsets);
+
 /* slot of `key` in a verification table with `mask`+1 slots (the device uses the same expression) */
 uint32_t kmpb_vtab_hash(uint32_t key, uint32_t mask);
 uint32_t kmpb_vtab_lens_slot(uint32_t first2);

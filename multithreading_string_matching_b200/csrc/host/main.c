@@ -11,8 +11,9 @@
  * perror("error opening file: ") + exit 1 (serial.c:60-63); an unreadable pcap is "error reading pcap
  * file: ..." on stderr + exit 1 (serial.c:92-95).  Throughput figures go to stderr when KMPB_STATS=1.
  *
- * With <n> > 1 the packets are split as mpi_dumping.c:149-157 splits them over ranks, one host
- * thread drives each GPU, and the per-pattern count vectors are summed (mpi_dumping.c:202).
+ * One host thread drives each GPU: it builds the context while the main thread frames the savefile,
+ * then streams its share of the packets (split as mpi_dumping.c:149-157 splits them over ranks) through
+ * kmpb_count_pcap; the per-pattern count vectors are summed at the end (mpi_dumping.c:202).
  */
 #include <errno.h>
 #include <pthread.h>
@@ -30,25 +31,44 @@ static double now_seconds(void)
     return (double)tv.tv_sec + (double)tv.tv_usec / 1e6;
 }
 
+/* What the GPU threads wait for: the savefile index (or the news that it could not be read). */
+typedef struct {
+    pthread_mutex_t lock;
+    pthread_cond_t ready;
+    const kmpb_pcap *pc;
+    int done, n_gpus;
+} ingest_gate;
+
 typedef struct {
     int device;
     const kmpb_patterns *pats;
-    const kmpb_csr *csr;
-    uint64_t first, count;
+    ingest_gate *gate;
     uint64_t *counts;
+    double start;
     int rc;
     char err[512];
 } shard_job;
 
+/* One host thread per GPU: the context and the pattern tables are built while the main thread frames
+ * the savefile; then the GPU's share of the packets (mpi_dumping.c:149-157) streams through it. */
 static void *run_shard(void *arg)
 {
     shard_job *job = arg;
     kmpb_ctx *ctx = NULL;
     job->rc = kmpb_create(&ctx, job->device);
     if (job->rc == 0) job->rc = kmpb_set_patterns(ctx, job->pats->blob, job->pats->pat_off, job->pats->n_pat);
-    if (job->rc == 0)
-        job->rc = kmpb_count_host(ctx, job->csr->bytes, job->csr->offsets + job->first, job->count, job->counts);
     if (job->rc != 0) snprintf(job->err, sizeof job->err, "%s", kmpb_last_error());
+    if (getenv("KMPB_STATS")) fprintf(stderr, "kmp_match: GPU %d context and pattern tables ready %.3f s after start\n", job->device, now_seconds() - job->start);
+    pthread_mutex_lock(&job->gate->lock);
+    while (!job->gate->done) pthread_cond_wait(&job->gate->ready, &job->gate->lock);
+    const kmpb_pcap *pc = job->gate->pc;
+    pthread_mutex_unlock(&job->gate->lock);
+    if (job->rc == 0 && pc != NULL) {
+        uint64_t first, count;
+        kmpb_shard_range(kmpb_pcap_packets(pc), (uint32_t)job->gate->n_gpus, (uint32_t)job->device, &first, &count);
+        job->rc = kmpb_count_pcap(ctx, pc, first, count, job->counts);
+        if (job->rc != 0) snprintf(job->err, sizeof job->err, "%s", kmpb_last_error());
+    }
     kmpb_destroy(ctx);
     return NULL;
 }
@@ -96,27 +116,39 @@ int main(int argc, char **argv)
     if (n_gpus > available) n_gpus = available;
 
     double start = now_seconds();
-    kmpb_csr csr;
-    rc = kmpb_load_pcap_csr(argv[1], proto, 1, &csr);
-    if (rc != 0) {
-        fprintf(stderr, "error reading pcap file: %s\n", kmpb_last_error());
-        return 1;
-    }
-
+    ingest_gate gate;
+    pthread_mutex_init(&gate.lock, NULL);
+    pthread_cond_init(&gate.ready, NULL);
+    gate.pc = NULL;
+    gate.done = 0;
+    gate.n_gpus = n_gpus;
     uint64_t *counts = calloc(pats.n_pat ? pats.n_pat : 1, sizeof *counts);
     shard_job *jobs = calloc((size_t)n_gpus, sizeof *jobs);
     pthread_t *threads = calloc((size_t)n_gpus, sizeof *threads);
     for (int g = 0; g < n_gpus; g++) {
         jobs[g].device = g;
         jobs[g].pats = &pats;
-        jobs[g].csr = &csr;
-        kmpb_shard_range(csr.n_packets, (uint32_t)n_gpus, (uint32_t)g, &jobs[g].first, &jobs[g].count);
+        jobs[g].gate = &gate;
+        jobs[g].start = start;
         jobs[g].counts = calloc(pats.n_pat ? pats.n_pat : 1, sizeof(uint64_t));
-        if (g > 0) pthread_create(&threads[g], NULL, run_shard, &jobs[g]);
+        pthread_create(&threads[g], NULL, run_shard, &jobs[g]);
     }
-    run_shard(&jobs[0]);
+    kmpb_pcap *pc = NULL;
+    rc = kmpb_pcap_open(argv[1], proto, &pc);
+    if (getenv("KMPB_STATS")) fprintf(stderr, "kmp_match: savefile framed in %.3f s\n", now_seconds() - start);
+    char open_err[512] = "";
+    if (rc != 0) snprintf(open_err, sizeof open_err, "%s", kmpb_last_error());
+    pthread_mutex_lock(&gate.lock);
+    gate.pc = pc;
+    gate.done = 1;
+    pthread_cond_broadcast(&gate.ready);
+    pthread_mutex_unlock(&gate.lock);
+    for (int g = 0; g < n_gpus; g++) pthread_join(threads[g], NULL);
+    if (rc != 0) {
+        fprintf(stderr, "error reading pcap file: %s\n", open_err);
+        return 1;
+    }
     for (int g = 0; g < n_gpus; g++) {
-        if (g > 0) pthread_join(threads[g], NULL);
         if (jobs[g].rc != 0) {
             fprintf(stderr, "error: GPU %d: %s\n", g, jobs[g].err);
             return 1;
@@ -132,15 +164,15 @@ int main(int argc, char **argv)
         double s = finish - start;
         fprintf(stderr, "kmp_match: %llu frames, %llu payloads, %llu payload bytes, %u patterns, %d GPU(s): "
                         "%.3f GB/s, %.3f Mpackets/s end to end (file read + pack + H2D + match)\n",
-                (unsigned long long)csr.n_frames, (unsigned long long)csr.n_packets,
-                (unsigned long long)csr.total_bytes, pats.n_pat, n_gpus,
-                (double)csr.total_bytes / s / 1e9, (double)csr.n_packets / s / 1e6);
+                (unsigned long long)kmpb_pcap_frames(pc), (unsigned long long)kmpb_pcap_packets(pc),
+                (unsigned long long)kmpb_pcap_bytes(pc), pats.n_pat, n_gpus,
+                (double)kmpb_pcap_bytes(pc) / s / 1e9, (double)kmpb_pcap_packets(pc) / s / 1e6);
     }
     for (int g = 0; g < n_gpus; g++) free(jobs[g].counts);
     free(jobs);
     free(threads);
     free(counts);
-    kmpb_free_csr(&csr);
+    kmpb_pcap_close(pc);
     kmpb_free_patterns(&pats);
     return 0;
 }

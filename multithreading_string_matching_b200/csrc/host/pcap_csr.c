@@ -115,11 +115,18 @@ static void pack_payloads(const uint8_t *file, const payload_ref *refs, uint64_t
     free(block_base);
 }
 
-int kmpb_load_pcap_csr(const char *path, int proto, int pinned, kmpb_csr *out)
+struct kmpb_pcap {
+    const uint8_t *file;
+    size_t size;
+    payload_ref *refs;
+    uint64_t n_packets, n_frames, total_bytes;
+};
+
+int kmpb_pcap_open(const char *path, int proto, kmpb_pcap **out)
 {
-    if (path == NULL || out == NULL) return kmpb_fail(KMPB_EINVAL, "kmpb_load_pcap_csr: NULL argument");
+    if (path == NULL || out == NULL) return kmpb_fail(KMPB_EINVAL, "kmpb_pcap_open: NULL argument");
+    *out = NULL;
     if (proto != KMPB_PROTO_UDP && proto != KMPB_PROTO_TCP) return kmpb_fail(KMPB_EINVAL, "unknown protocol %d", proto);
-    memset(out, 0, sizeof *out);
     int fd = open(path, O_RDONLY);
     struct stat st;
     if (fd < 0 || fstat(fd, &st) != 0) {
@@ -150,36 +157,71 @@ int kmpb_load_pcap_csr(const char *path, int proto, int pinned, kmpb_csr *out)
         return kmpb_fail(KMPB_EFORMAT, "unknown file format");
     }
     extract_fn extract = proto == KMPB_PROTO_TCP ? kmpb_extract_tcp : kmpb_extract_udp;
-
-    uint64_t n = 0, frames = 0, total = 0;
-    payload_ref *refs = NULL;
-    if (index_records(file, size, swapped, extract, &refs, &n, &frames, &total) != KMPB_OK) {
+    kmpb_pcap *pc = calloc(1, sizeof *pc);
+    if (pc == NULL || index_records(file, size, swapped, extract, &pc->refs, &pc->n_packets, &pc->n_frames, &pc->total_bytes) != KMPB_OK) {
+        free(pc);
         munmap((void *)file, size);
         return kmpb_fail(KMPB_ENOMEM, "out of memory indexing %s", path);
     }
+    pc->file = file;
+    pc->size = size;
+    *out = pc;
+    return KMPB_OK;
+}
 
+void kmpb_pcap_close(kmpb_pcap *pc)
+{
+    if (pc == NULL) return;
+    free(pc->refs);
+    if (pc->file) munmap((void *)pc->file, pc->size);
+    free(pc);
+}
+
+uint64_t kmpb_pcap_packets(const kmpb_pcap *pc) { return pc ? pc->n_packets : 0; }
+uint64_t kmpb_pcap_frames(const kmpb_pcap *pc) { return pc ? pc->n_frames : 0; }
+uint64_t kmpb_pcap_bytes(const kmpb_pcap *pc) { return pc ? pc->total_bytes : 0; }
+
+uint64_t kmpb_pcap_chunk_end(const kmpb_pcap *pc, uint64_t first, uint64_t last, uint64_t max_bytes, uint64_t max_packets,
+                             uint64_t *bytes_out)
+{
+    uint64_t k = first, bytes = 0;
+    while (k < last && k - first < max_packets && (k == first || bytes + pc->refs[k].len <= max_bytes)) bytes += pc->refs[k++].len;
+    if (bytes_out) *bytes_out = bytes;
+    return k;
+}
+
+void kmpb_pcap_pack(const kmpb_pcap *pc, uint64_t first, uint64_t count, uint8_t *dst, uint64_t *offsets)
+{
+    pack_payloads(pc->file, pc->refs + first, count, dst, offsets);
+}
+
+int kmpb_load_pcap_csr(const char *path, int proto, int pinned, kmpb_csr *out)
+{
+    if (path == NULL || out == NULL) return kmpb_fail(KMPB_EINVAL, "kmpb_load_pcap_csr: NULL argument");
+    memset(out, 0, sizeof *out);
+    kmpb_pcap *pc = NULL;
+    int rc = kmpb_pcap_open(path, proto, &pc);
+    if (rc != KMPB_OK) return rc;
+    const uint64_t n = pc->n_packets, total = pc->total_bytes;
     size_t bytes_sz = (size_t)total + CSR_TAIL_PAD, off_sz = (size_t)(n + 1) * sizeof(uint64_t);
     uint8_t *bytes = pinned ? kmpb_host_alloc(bytes_sz) : malloc(bytes_sz);
     uint64_t *offsets = pinned ? kmpb_host_alloc(off_sz) : malloc(off_sz);
     if (bytes == NULL || offsets == NULL) {
         if (pinned) { kmpb_host_free(bytes); kmpb_host_free(offsets); }
         else { free(bytes); free(offsets); }
-        munmap((void *)file, size);
-        free(refs);
+        kmpb_pcap_close(pc);
         return kmpb_fail(KMPB_ENOMEM, "cannot allocate %zu bytes of %s memory for the payload batch",
                          bytes_sz + off_sz, pinned ? "pinned" : "host");
     }
-    pack_payloads(file, refs, n, bytes, offsets);
-    free(refs);
+    pack_payloads(pc->file, pc->refs, n, bytes, offsets);
     memset(bytes + total, 0, CSR_TAIL_PAD);
-    munmap((void *)file, size);
-
     out->bytes = bytes;
     out->offsets = offsets;
     out->n_packets = n;
-    out->n_frames = frames;
+    out->n_frames = pc->n_frames;
     out->total_bytes = total;
     out->pinned = pinned ? 1 : 0;
+    kmpb_pcap_close(pc);
     return KMPB_OK;
 }
 

@@ -188,6 +188,21 @@ class Matcher:
         finally:
             batch.close()
 
+    def count_pcap_streamed(self, path, proto="udp", first=0, count=None):
+        """serial.c:91-155 in one pass over the savefile: batches of payloads are packed into pinned staging
+        buffers and matched while the next batch is packed (kmpb_pcap_open + kmpb_count_pcap).  `first`,
+        `count` select a slice of the accepted packets (a rank's share); default: all of them."""
+        pc = ctypes.c_void_p()
+        check(lib().kmpb_pcap_open(os.fsencode(path), _PROTO[proto], ctypes.byref(pc)))
+        try:
+            n = lib().kmpb_pcap_packets(pc)
+            count = n - first if count is None else count
+            counts = np.zeros(max(len(self.patterns), 1), dtype=np.uint64)
+            check(lib().kmpb_count_pcap(self._ctx, pc, first, count, counts.ctypes.data_as(c_u64p)))
+            return counts[: len(self.patterns)].tolist()
+        finally:
+            lib().kmpb_pcap_close(pc)
+
     @property
     def launches(self):
         return lib().kmpb_launch_count(self._ctx)

@@ -59,6 +59,43 @@ def test_bundled_pcaps_bit_exact_vs_serial_c(matchers, strings, engine, pcap, pr
     assert kmp.format_report(strings, counts) == expected
 
 
+@pytest.mark.parametrize("pcap,proto,expected", golden_runs(), ids=lambda v: v if isinstance(v, str) else "")
+def test_bundled_pcaps_streamed_path(matchers, strings, pcap, proto, expected):
+    """The fused ingest + match path (kmpb_pcap_open / kmpb_count_pcap, what bin/kmp_match runs)."""
+    m = matchers["union"]
+    m.set_patterns(strings)
+    counts = m.count_pcap_streamed(os.path.join(DATA, pcap + ".pcap"), proto)
+    assert kmp.format_report(strings, counts) == expected
+
+
+def test_streamed_path_chunks_and_slices(matchers, oracle, strings, tmp_path):
+    """Many small staging chunks (the slot ring wraps many times) and rank slices that add up."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from multithreading_string_matching_b200 import distributed as kd
+
+    synth = kmp.Synth(seed=23, len_mode=1, plants=2, plant_patterns=strings)
+    data, off = synth.fill_host(0, 12_000)
+    path = str(tmp_path / "mixed.pcap")
+    bench.write_pcap(path, data, off)
+    m = matchers["union"]
+    m.set_patterns(strings)
+    want = oracle.count_csr(data, off, strings)
+    os.environ["KMPB_CHUNK_MB"] = "1"
+    try:
+        assert m.count_pcap_streamed(path) == want
+        for world in (2, 3):
+            acc = [0] * len(strings)
+            for rank in range(world):
+                first, count = kd.rank_slice(12_000, rank, world)
+                acc = [a + b for a, b in zip(acc, m.count_pcap_streamed(path, first=first, count=count))]
+            assert acc == want, world
+    finally:
+        del os.environ["KMPB_CHUNK_MB"]
+    assert m.count_pcap_streamed(path) == want
+
+
 def test_cli_output_is_the_reference_output(strings):
     exe = os.path.join(ROOT, "multithreading_string_matching_b200", "bin", "kmp_match")
     for pcap, proto, expected in golden_runs():
