@@ -67,8 +67,8 @@ constexpr uint32_t UN_LUT_BYTES = 256 * 256; // 256-byte row per byte value; lan
 constexpr uint32_t FULL = 0xffffffffu;
 
 // Dynamic shared memory.  The LUT must start at a 64 KB-aligned shared address; the gap in front of it
-// (63 KB when the dynamic window starts at 0x400, the usual case) holds the event lists, the counters
-// and the verification tables; the per-warp row rings follow the LUT.
+// (63 KB when the dynamic window starts at 0x400, the usual case) holds the event lists and the counters;
+// the per-warp row rings follow the LUT, the verification tables follow the rings (as long as they fit).
 constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_WORDS * 4;
 constexpr uint32_t UN_RING_BYTES = UN_WARPS * UN_SLOTS * UN_SLOT_BYTES;
 constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
@@ -76,7 +76,8 @@ constexpr uint32_t UN_FRONT_FIXED = UN_Q_BYTES + UN_SCRATCH_BYTES + 16;
 constexpr uint32_t UN_FRONT_MAX = 60 * 1024; // what the gap is trusted to hold
 constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_RING_BYTES;
 static_assert(UN_FRONT_FIXED + 1024 <= UN_FRONT_MAX, "event lists do not fit in front of the LUT");
-static_assert(UN_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr size_t UN_SMEM_MAX = 227 * 1024; // opt-in shared memory of one block on sm_100
+static_assert(UN_SMEM_BYTES <= UN_SMEM_MAX, "shared memory budget");
 
 struct union_params {
     const uint8_t *bytes; // device pointer to absolute byte abs_base (abs_base % 512 == 0)
@@ -452,8 +453,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     const uint32_t lut_off = (0x10000u - (dyn_saddr & 0xffffu)) & 0xffffu;
     const uint32_t counts_bytes = p.counts_in_smem ? ((4u * p.n_uniq + 15u) & ~15u) : 0u;
     const uint32_t vtab_bytes = p.vtab_in_smem ? 4u * p.vtab_words : 0u;
-    const uint32_t front_bytes = UN_FRONT_FIXED + counts_bytes + vtab_bytes;
-    if (lut_off < front_bytes || lut_off + UN_LUT_BYTES + UN_RING_BYTES > dyn_size) {
+    const uint32_t front_bytes = UN_FRONT_FIXED + counts_bytes;
+    if (lut_off < front_bytes || lut_off + UN_LUT_BYTES + UN_RING_BYTES + vtab_bytes > dyn_size) {
         // unexpected shared-memory window base: refuse rather than compute something wrong
         if (threadIdx.x == 0) atomicOr(&p.work[1], 2u);
         return;
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     uint8_t *scratch_all = smem + UN_Q_BYTES;
     uint32_t *s_lut_saddr = reinterpret_cast<uint32_t *>(scratch_all + UN_SCRATCH_BYTES);
     uint32_t *s_counts = reinterpret_cast<uint32_t *>(s_lut_saddr + 4);
-    uint32_t *s_vtab = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_counts) + counts_bytes);
+    uint32_t *s_vtab = reinterpret_cast<uint32_t *>(ring_all + UN_RING_BYTES); // behind the rings
 
     for (uint32_t i = threadIdx.x; i < 256 * 32; i += UN_THREADS)
         reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + (i & 31)] = p.filter[i >> 5];
@@ -674,13 +675,15 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     uint32_t *d_items = ctx->d_items + (size_t)slot * ctx->items_cap;
     uint32_t *d_work = ctx->d_work + slot * 4;
 
-    // what fits in the shared-memory gap in front of the LUT: counters first, then the hash tables
+    // the counters go into the shared-memory gap in front of the LUT if they fit, the hash tables behind
+    // the row rings if the block's 227 KB allow it (the LUT may start up to 64 KB into the allocation)
     uint32_t front = UN_FRONT_FIXED;
     const bool counts_in_smem = front + 4ull * h.n_uniq + 16 <= UN_FRONT_MAX;
     if (counts_in_smem) front += (4u * h.n_uniq + 15u) & ~15u;
-    const bool vtab_in_smem = front + 4ull * h.vtab_words <= UN_FRONT_MAX;
+    const bool vtab_in_smem = UN_SMEM_BYTES + 4ull * h.vtab_words <= UN_SMEM_MAX;
+    const size_t smem_bytes = UN_SMEM_BYTES + (vtab_in_smem ? 4ull * h.vtab_words : 0);
     if (!ctx->attr_union_set) {
-        KMPB_CUDA(cudaFuncSetAttribute(kmpb_union_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UN_SMEM_BYTES));
+        KMPB_CUDA(cudaFuncSetAttribute(kmpb_union_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UN_SMEM_MAX));
         ctx->attr_union_set = true;
     }
     kmpb_union_partition_kernel<<<(n_items + 1 + 255) / 256, 256, 0, stream>>>(b.d_offsets, (uint32_t)b.n_packets, n_items,
@@ -705,7 +708,7 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     int grid = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, (warps_needed + UN_WARPS - 1) / UN_WARPS);
     if (grid < 1) grid = 1;
     if (ctx->profile) KMPB_CUDA(cudaEventRecord(ctx->ev_kernel[0], stream));
-    kmpb_union_kernel<<<grid, UN_THREADS, UN_SMEM_BYTES, stream>>>(p);
+    kmpb_union_kernel<<<grid, UN_THREADS, smem_bytes, stream>>>(p);
     if (ctx->profile) KMPB_CUDA(cudaEventRecord(ctx->ev_kernel[1], stream));
     ctx->launches += 2;
     KMPB_CUDA(cudaGetLastError());
