@@ -46,7 +46,7 @@
 #include "kmpb_device.cuh"
 
 #ifndef KMPB_UN_THREADS
-#define KMPB_UN_THREADS 1024
+#define KMPB_UN_THREADS 896
 #endif
 #ifndef KMPB_UN_ITEM_KB
 #define KMPB_UN_ITEM_KB 64

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Process-level comparison on one synthetic pcap (the reference's surface: <pcap> <strings.txt> ...):
+"""Checker-side tool (under tests/ because it executes the reference binaries of oracle/_ref).
+Process-level comparison on one synthetic pcap (the reference's surface: <pcap> <strings.txt> ...):
 bin/kmp_match vs the unmodified reference programs built under oracle/_ref.  Prints wall time of each
 whole process, the time each program reports itself, and whether the count lines are identical."""
 import os
