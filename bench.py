@@ -329,7 +329,39 @@ def ours(args, kmp, patterns):
     reduced = [None, None]
     step_no = [0]
 
+    # Reduce across GPUs.  Preferred: every rank's count vectors live in symmetric memory (mapped into all
+    # ranks over NVLink) and the match kernel's last block adds its counts straight into all of them --
+    # no collective call at all (kmpb_count_device_span_peers).  One row of counts per step, so no rank
+    # ever clears a vector another rank may be adding to.  Fallback: one NCCL all-reduce per step on a
+    # side stream, overlapped with the next step's kernel.
+    p2p = None
+    if world > 1 and args.reduce != "nccl" and args.engine == "union":
+        ok, why = 1, ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            rows = args.warmup + args.steps + 16
+            sym = symm.empty((rows, n_pat), dtype=torch.int64, device=dev)
+            sym.zero_()
+            hdl = symm.rendezvous(sym, dist.group.WORLD)
+            peer_ptrs = [int(hdl.buffer_ptrs[r]) for r in range(world)]
+        except Exception as e:  # no symmetric memory on this box / build
+            ok, why = 0, repr(e)[:200]
+        agree = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) == 1:
+            p2p = {"sym": sym, "ptrs": peer_ptrs, "rows": rows}
+        elif rank == 0 and why:
+            print("bench: symmetric memory unavailable, using NCCL all-reduce: " + why, file=sys.stderr)
+        torch.cuda.synchronize()
+        dist.barrier()
+
     def step():
+        if p2p is not None:
+            row = step_no[0] % p2p["rows"]
+            step_no[0] += 1
+            vecs = [ptr + row * n_pat * 8 for ptr in p2p["ptrs"]]
+            m.count_device_into(d_bytes.data_ptr(), d_off.data_ptr(), count, vecs, span=(0, nbytes), stream=stream.cuda_stream)
+            return p2p["sym"][row]
         i = step_no[0] & 1
         step_no[0] += 1
         buf = d_counts2[i]
@@ -349,7 +381,7 @@ def ours(args, kmp, patterns):
         return buf
 
     def drain_side():
-        if world > 1:
+        if world > 1 and p2p is None:
             stream.wait_stream(side)
 
     def barrier():
@@ -462,7 +494,10 @@ def ours(args, kmp, patterns):
             "config": {"workload": "synthetic UDP pcap, %d packets x %d B payloads per GPU, bundled strings.txt (97 patterns, 87 distinct)"
                                    % (per_gpu, L),
                        "packets_total": total_packets, "payload_bytes_total": int(total_bytes), "engine": args.engine,
-                       "split": "mpi_dumping.c:149-157 contiguous packet slices, counts summed by one NCCL all-reduce per step (side stream, overlapped with the next step's kernel)",
+                       "split": "mpi_dumping.c:149-157 contiguous packet slices",
+                       "reduce": ("none (one GPU)" if world == 1 else
+                                  "in the match kernel: its last block adds the counts to every rank's vector in symmetric memory over NVLink (no collective call)"
+                                  if p2p is not None else "one NCCL all-reduce per step on a side stream, overlapped with the next step's kernel"),
                        "l2": "inputs (%.1f GB per GPU) larger than the 126 MB L2; no flush needed" % (nbytes / 1e9)},
             "packets_per_s": total_packets / (ms_step / 1e3),
             "hbm_frac_of_measured_peak": value / world / peak,
@@ -510,6 +545,7 @@ def main():
     ap.add_argument("--payload-len", type=int, default=1400)
     ap.add_argument("--engine", default="union", choices=["union", "perpat"])
     ap.add_argument("--ref-packets", type=int, default=0, help="CPU sample size (0 = calibrate to ~10 s)")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "nccl"], help="N>1: in-kernel reduce over symmetric memory, or NCCL")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

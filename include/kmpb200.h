@@ -115,6 +115,15 @@ int kmpb_count_device(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_o
 int kmpb_count_device_span(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets,
                            uint64_t n_packets, uint64_t first_byte, uint64_t end_byte,
                            uint64_t *d_counts, void *stream);
+/* Same, with the reduce across GPUs inside the match kernel: the counts are added to n_vectors (1..8)
+ * count vectors of uint64[n_pat] -- this GPU's own and those of its peers, mapped into this process
+ * over NVLink (CUDA IPC / symmetric memory) -- by system-scope atomics issued by the kernel's last
+ * block.  Replaces the local merge (openmp_data.c:169-173) plus MPI_Reduce(SUM) (mpi_dumping.c:202)
+ * for device-resident callers: when every rank has passed its own batch, every vector holds the
+ * total.  The caller orders "all ranks have finished" (a barrier) before reading a vector. */
+int kmpb_count_device_span_peers(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets,
+                                 uint64_t n_packets, uint64_t first_byte, uint64_t end_byte,
+                                 uint64_t *const *d_counts_all, uint32_t n_vectors, void *stream);
 /* Device copy of the per-pattern counts of the last kmpb_count_host call (uint64[n_pat] on the
  * context's GPU), for callers that combine several GPUs with a collective (mpi_dumping.c:202). */
 uint64_t *kmpb_device_counts(kmpb_ctx *ctx);

@@ -51,6 +51,9 @@ SIGNATURES = {
                                          ctypes.c_void_p, ctypes.c_void_p]),
     "kmpb_count_device_span": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
                                               ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]),
+    "kmpb_count_device_span_peers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                                   ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p),
+                                                   ctypes.c_uint32, ctypes.c_void_p]),
     "kmpb_device_counts": (ctypes.c_void_p, [ctypes.c_void_p]),
     "kmpb_set_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "kmpb_last_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),

@@ -256,15 +256,21 @@ int kmpb_get_prefix(kmpb_ctx *ctx, uint32_t pattern_index, int32_t *pi_out, uint
     return KMPB_OK;
 }
 
-// Device-resident batch with the byte span given by the caller: fully asynchronous.
-int kmpb_count_device_span(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_packets,
-                           uint64_t first_byte, uint64_t end_byte, uint64_t *d_counts, void *stream_v)
+// Device-resident batch with the byte span given by the caller: fully asynchronous.  The counts are added to
+// n_vectors count vectors (this GPU's and/or NVLink-mapped peers'); with the union engine the kernel's
+// last block does that itself, so a pass is two launches (work partition, match) and no collective.
+static int count_device_span_into(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_packets,
+                                  uint64_t first_byte, uint64_t end_byte, uint64_t *const *d_counts, uint32_t n_vectors,
+                                  void *stream_v)
 {
     if (ctx == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL context");
     if (!ctx->have_tables) return kmpb_fail(KMPB_ESTATE, "count before kmpb_set_patterns");
     if (ctx->host.n_pat == 0) return KMPB_OK;
-    if (d_counts == nullptr || (n_packets && (d_bytes == nullptr || d_offsets == nullptr)))
-        return kmpb_fail(KMPB_EINVAL, "NULL device pointer");
+    if (d_counts == nullptr || n_vectors == 0 || n_vectors > (uint32_t)KMPB_MAX_OUT)
+        return kmpb_fail(KMPB_EINVAL, "1..%d count vectors expected", KMPB_MAX_OUT);
+    for (uint32_t r = 0; r < n_vectors; r++)
+        if (d_counts[r] == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL device pointer");
+    if (n_packets && (d_bytes == nullptr || d_offsets == nullptr)) return kmpb_fail(KMPB_EINVAL, "NULL device pointer");
     if (end_byte < first_byte) return kmpb_fail(KMPB_EINVAL, "offsets decrease");
     int rc = use_device(ctx);
     if (rc) return rc;
@@ -273,13 +279,36 @@ int kmpb_count_device_span(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t
     const uint32_t nu = ctx->host.n_uniq;
     KMPB_CUDA(cudaMemsetAsync(ctx->d_uniq_counts, 0, (size_t)nu * sizeof(uint64_t), stream));
     kmpb_batch b{d_bytes, 0, d_offsets, n_packets, first_byte, end_byte};
+    const bool fused = ctx->engine != KMPB_ENGINE_PERPAT && n_packets > 0 && end_byte > first_byte && nu > 0;
+    if (fused) {
+        kmpb_fused_out out;
+        out.n = n_vectors;
+        for (uint32_t r = 0; r < n_vectors; r++) out.vec[r] = (unsigned long long *)d_counts[r];
+        return kmpb_launch_union(ctx, b, 0, ctx->d_uniq_counts, stream, out);
+    }
     if ((rc = run_engine(ctx, b, 0, stream))) return rc;
-    kmpb_expand_counts_kernel<<<(ctx->host.n_pat + 255) / 256, 256, 0, stream>>>(
-        (const unsigned long long *)ctx->d_uniq_counts, nu, 1, ctx->dev.pat_to_uniq, ctx->host.n_pat,
-        (unsigned long long *)d_counts, 1);
-    ctx->launches++;
+    for (uint32_t r = 0; r < n_vectors; r++) {
+        kmpb_expand_counts_kernel<<<(ctx->host.n_pat + 255) / 256, 256, 0, stream>>>(
+            (const unsigned long long *)ctx->d_uniq_counts, nu, 1, ctx->dev.pat_to_uniq, ctx->host.n_pat,
+            (unsigned long long *)d_counts[r], 1);
+        ctx->launches++;
+    }
     KMPB_CUDA(cudaGetLastError());
     return KMPB_OK;
+}
+
+int kmpb_count_device_span(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_packets,
+                           uint64_t first_byte, uint64_t end_byte, uint64_t *d_counts, void *stream_v)
+{
+    uint64_t *one[1] = {d_counts};
+    return count_device_span_into(ctx, d_bytes, d_offsets, n_packets, first_byte, end_byte, one, 1, stream_v);
+}
+
+int kmpb_count_device_span_peers(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_packets,
+                                 uint64_t first_byte, uint64_t end_byte, uint64_t *const *d_counts_all,
+                                 uint32_t n_vectors, void *stream_v)
+{
+    return count_device_span_into(ctx, d_bytes, d_offsets, n_packets, first_byte, end_byte, d_counts_all, n_vectors, stream_v);
 }
 
 int kmpb_count_device(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_packets,

@@ -81,13 +81,22 @@ struct kmpb_batch {
     uint64_t first_byte, end_byte; // offsets[0], offsets[n_packets] (host copies)
 };
 
+// Where the union kernel's last block adds the per-pattern counts (file order) itself: up to 8 count
+// vectors, this GPU's and/or peers' mapped over NVLink.  n = 0: the caller expands the counts afterwards.
+constexpr int KMPB_MAX_OUT = 8;
+struct kmpb_fused_out {
+    unsigned long long *vec[KMPB_MAX_OUT] = {};
+    uint32_t n = 0;
+};
+
 // tables.cu
 int kmpb_upload_tables(kmpb_ctx *ctx);
 void kmpb_release_tables(kmpb_ctx *ctx);
 // perpat_kernel.cu
 int kmpb_launch_perpat(kmpb_ctx *ctx, const kmpb_batch &b, uint64_t *d_uniq_counts, cudaStream_t stream);
 // union_kernel.cu
-int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_uniq_counts, cudaStream_t stream);
+int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_uniq_counts, cudaStream_t stream,
+                      const kmpb_fused_out &out = kmpb_fused_out());
 int kmpb_union_scratch(kmpb_ctx *ctx, uint64_t max_batch_bytes);
 // api.cu
 int kmpb_launch_expand(kmpb_ctx *ctx, const uint64_t *d_uniq_counts, uint64_t *d_counts, cudaStream_t stream);

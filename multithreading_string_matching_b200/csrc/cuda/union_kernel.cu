@@ -96,6 +96,11 @@ struct union_params {
     uint32_t mul256; // the value 256, passed at run time so the shift-or-0xff compiles to an integer
                      // multiply-add on the FMA pipe instead of competing for the ALU pipe
     unsigned long long *uniq_counts;
+    // fused expansion + reduction (n_out > 0): the last block to finish adds every pattern's count, in file
+    // order, to out[0..n_out) -- this GPU's count vector and/or its peers' (NVLink-mapped)
+    const uint32_t *pat_to_uniq;
+    uint32_t n_pat, n_out;
+    unsigned long long *out[KMPB_MAX_OUT];
 };
 
 // ---- work partition: item i = packets [items[i], items[i+1]) ---------------------------------
@@ -104,7 +109,7 @@ __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets
                                             uint32_t *__restrict__ work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { work[0] = 0; work[1] = 0; }
+    if (i == 0) { work[0] = 0; work[1] = 0; work[2] = 0; }
     if (i > n_items) return;
     if (i == n_items) { items[i] = n_packets; return; }
     // first packet whose start is >= offsets[0] + i * item_bytes
@@ -642,6 +647,25 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     if (p.counts_in_smem)
         for (uint32_t u = threadIdx.x; u < p.n_uniq; u += UN_THREADS)
             if (s_counts[u]) atomicAdd(p.uniq_counts + u, (unsigned long long)s_counts[u]);
+
+    // The merge of the partial counts (openmp_data.c:169-173) and, across GPUs, the MPI_Reduce(SUM) of
+    // mpi_dumping.c:202, inside this kernel: the last block to arrive expands the distinct-pattern totals
+    // to file order and adds them to every count vector it was given -- system-scope atomics, so a vector
+    // may live in a peer GPU's memory.
+    if (p.n_out) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_lut_saddr[1] = atomicAdd(&p.work[2], 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (s_lut_saddr[1]) {
+            __threadfence();
+            for (uint32_t i = threadIdx.x; i < p.n_pat; i += UN_THREADS) {
+                const unsigned long long v = __ldcg(p.uniq_counts + p.pat_to_uniq[i]);
+                if (v)
+                    for (uint32_t r = 0; r < p.n_out; r++) atomicAdd_system(p.out[r] + i, v);
+            }
+        }
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -660,7 +684,8 @@ int kmpb_union_scratch(kmpb_ctx *ctx, uint64_t max_batch_bytes)
     return KMPB_OK;
 }
 
-int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_uniq_counts, cudaStream_t stream)
+int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_uniq_counts, cudaStream_t stream,
+                      const kmpb_fused_out &out)
 {
     const kmpb_tables &h = ctx->host;
     if (h.n_uniq == 0 || b.n_packets == 0 || b.end_byte == b.first_byte) return KMPB_OK;
@@ -704,6 +729,10 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     p.vtab_words = h.vtab_words;
     p.mul256 = 256u;
     p.uniq_counts = (unsigned long long *)d_uniq_counts;
+    p.pat_to_uniq = ctx->dev.pat_to_uniq;
+    p.n_pat = h.n_pat;
+    p.n_out = out.n;
+    for (int r = 0; r < KMPB_MAX_OUT; r++) p.out[r] = out.vec[r];
     const uint32_t warps_needed = n_items;
     int grid = (int)std::min<uint32_t>((uint32_t)ctx->sm_count, (warps_needed + UN_WARPS - 1) / UN_WARPS);
     if (grid < 1) grid = 1;

@@ -180,6 +180,13 @@ class Matcher:
             check(lib().kmpb_count_device_span(self._ctx, d_bytes_ptr, d_offsets_ptr, n_packets, span[0], span[1],
                                                d_counts_ptr, stream))
 
+    def count_device_into(self, d_bytes_ptr, d_offsets_ptr, n_packets, count_vector_ptrs, span, stream=None):
+        """Device-resident form whose counts are added to several uint64[n_pat] vectors at once -- this GPU's
+        and its peers' (NVLink-mapped) -- by the match kernel itself: count + all-reduce in one launch."""
+        vecs = (ctypes.c_void_p * len(count_vector_ptrs))(*count_vector_ptrs)
+        check(lib().kmpb_count_device_span_peers(self._ctx, d_bytes_ptr, d_offsets_ptr, n_packets, span[0], span[1],
+                                                 vecs, len(count_vector_ptrs), stream))
+
     def count_pcap(self, path, proto="udp", pinned=True):
         batch = PayloadBatch(path, proto, pinned=pinned)
         try:

@@ -277,6 +277,29 @@ def test_synthetic_device_resident_stream(matchers, oracle, strings):
     assert p.count_host(sample, soff) == m.count_host(sample, soff) == oracle.count_csr(sample, soff, strings)
 
 
+def test_fused_reduce_into_several_vectors(matchers, oracle, strings):
+    """kmpb_count_device_span_peers: the kernel's last block adds the counts to every vector it is given
+    (on a multi-GPU box the other vectors are peers' memory; here they are local)."""
+    import torch
+
+    synth = kmp.Synth(seed=5, payload_len=700, plants=2, plant_patterns=strings)
+    data, off = synth.fill_host(0, 9000)
+    want = oracle.count_csr(data, off, strings)
+    m = matchers["union"]
+    m.set_patterns(strings)
+    d_bytes = torch.zeros(len(data) + 4096, dtype=torch.uint8, device="cuda:0")
+    d_bytes[: len(data)] = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    vecs = [torch.zeros(len(strings), dtype=torch.int64, device="cuda:0") for _ in range(3)]
+    vecs[2] += 7
+    for _ in range(2):
+        m.count_device_into(d_bytes.data_ptr(), d_off.data_ptr(), 9000, [v.data_ptr() for v in vecs], span=(0, int(off[-1])))
+    torch.cuda.synchronize()
+    assert vecs[0].cpu().tolist() == [2 * w for w in want]
+    assert vecs[1].cpu().tolist() == [2 * w for w in want]
+    assert vecs[2].cpu().tolist() == [2 * w + 7 for w in want]
+
+
 def test_mixed_length_stream_host_path(matchers, oracle, strings):
     """Config 5 shape at reduced size through the host (pinned, chunked H2D) entry point."""
     synth = kmp.Synth(seed=11, len_mode=1, plants=2, plant_patterns=strings)
