@@ -1,7 +1,9 @@
 """Multi-GPU plumbing: one process per GPU (torch.distributed), packets split over ranks exactly as
 the reference's MPI variant splits them (mpi_dumping.c:149-157), per-pattern count vectors summed with
 one all-reduce (the MPI_Reduce(SUM) of mpi_dumping.c:202 -- NCCL over NVLink on GPUs, gloo in CPU tests).
-There is no data-path collective: every rank reads (or generates) only its own contiguous slice."""
+There is no data-path collective: every rank reads (or generates) only its own contiguous slice.
+Device-resident callers can skip the collective altogether: Matcher.count_device_into adds a rank's counts
+to every rank's vector (symmetric memory) from inside the match kernel -- see bench.py."""
 import torch
 import torch.distributed as dist
 
