@@ -8,6 +8,7 @@
  * array -- the CSR batch the device consumes -- in pinned memory so the H2D copies can run
  * asynchronously.
  *
+ * Classic savefiles (either byte order, microsecond or nanosecond stamps) and pcapng files are read.
  * Frames are read with their captured length (openmp_data.c:114-116; serial.c:117-120 uses the wire
  * length, the same number whenever caplen == len).  Like the reference's `while (pcap_next_ex(...)
  * >= 0)` loop, a truncated trailing record ends the walk without an error.
@@ -41,39 +42,101 @@ typedef struct {
     uint32_t len;
 } payload_ref;
 
-/* Pass 1, sequential (record n+1 starts where record n's header says): frame the records, run the
- * extractor on every frame and remember where the accepted payloads are. */
-static int index_records(const uint8_t *file, size_t size, int swapped, extract_fn extract, payload_ref **refs_out,
-                         uint64_t *n_packets, uint64_t *n_frames, uint64_t *total)
+/* Growing list of accepted payloads. */
+typedef struct {
+    payload_ref *refs;
+    size_t cap;
+    uint64_t packets, frames, bytes;
+} ref_list;
+
+/* one frame of `caplen` captured bytes at file offset `at`: run the extractor, remember the payload */
+static int take_frame(ref_list *l, const uint8_t *file, size_t at, uint32_t caplen, extract_fn extract)
 {
-    size_t at = PCAP_GLOBAL_HDR, cap = 1u << 16;
-    uint64_t packets = 0, frames = 0, bytes = 0;
-    payload_ref *refs = malloc(cap * sizeof *refs);
-    if (!refs) return KMPB_ENOMEM;
+    uint32_t off, len;
+    l->frames++;
+    if (!extract(file + at, caplen, &off, &len)) return KMPB_OK;
+    if (l->packets == l->cap) {
+        size_t cap = l->cap ? 2 * l->cap : (size_t)1 << 16;
+        payload_ref *grown = realloc(l->refs, cap * sizeof *grown);
+        if (!grown) return KMPB_ENOMEM;
+        l->refs = grown;
+        l->cap = cap;
+    }
+    l->refs[l->packets].at = at + off;
+    l->refs[l->packets].len = len;
+    l->bytes += len;
+    l->packets++;
+    return KMPB_OK;
+}
+
+/* Pass 1 for a classic savefile, sequential (record n+1 starts where record n's header says): frame the
+ * records, run the extractor on every frame and remember where the accepted payloads are. */
+static int index_classic(const uint8_t *file, size_t size, int swapped, extract_fn extract, ref_list *l)
+{
+    size_t at = PCAP_GLOBAL_HDR;
     while (size - at >= PCAP_RECORD_HDR) {
         uint32_t caplen = load32(file + at + 8, swapped);
         at += PCAP_RECORD_HDR;
         if (caplen > size - at) break; /* truncated record: libpcap reports an error, the loop ends */
-        uint32_t off, len;
-        frames++;
-        if (extract(file + at, caplen, &off, &len)) {
-            if (packets == cap) {
-                payload_ref *grown = realloc(refs, 2 * cap * sizeof *refs);
-                if (!grown) { free(refs); return KMPB_ENOMEM; }
-                refs = grown;
-                cap *= 2;
-            }
-            refs[packets].at = at + off;
-            refs[packets].len = len;
-            bytes += len;
-            packets++;
-        }
+        if (take_frame(l, file, at, caplen, extract) != KMPB_OK) return KMPB_ENOMEM;
         at += caplen;
     }
-    *refs_out = refs;
-    *n_packets = packets;
-    *n_frames = frames;
-    *total = bytes;
+    return KMPB_OK;
+}
+
+/* Pass 1 for a pcapng file (what libpcap's pcap_next_ex hands out when pcap_open_offline meets one, SURVEY
+ * 8f-3): blocks of [type, total length, body, total length], 32-bit aligned; a Section Header Block sets
+ * the byte order of its section; packets come from Enhanced (6), Simple (3) and obsolete Packet (2)
+ * blocks; everything else (interface descriptions, name resolution, statistics, ...) is skipped.  A
+ * malformed or truncated block ends the walk, like a truncated record does. */
+#define NG_SHB 0x0a0d0d0au
+#define NG_BYTE_ORDER 0x1a2b3c4du
+static int index_pcapng(const uint8_t *file, size_t size, extract_fn extract, ref_list *l)
+{
+    size_t at = 0;
+    int swapped = 0;
+    uint32_t snaplen0 = 0; /* snaplen of interface 0, for Simple Packet Blocks */
+    int have_if0 = 0;
+    while (size - at >= 12) {
+        uint32_t type_raw;
+        memcpy(&type_raw, file + at, 4);
+        if (type_raw == NG_SHB) { /* palindromic: readable before the byte order is known */
+            if (size - at < 28) break;
+            uint32_t bom;
+            memcpy(&bom, file + at + 8, 4);
+            if (bom == NG_BYTE_ORDER) swapped = 0;
+            else if (__builtin_bswap32(bom) == NG_BYTE_ORDER) swapped = 1;
+            else break;
+            have_if0 = 0;
+        }
+        const uint32_t type = type_raw == NG_SHB ? NG_SHB : load32(file + at, swapped);
+        const uint32_t total = load32(file + at + 4, swapped);
+        if (total < 12 || (total & 3u) || total > size - at) break;
+        const size_t body = at + 8, body_len = total - 12;
+        if (type == 1u) { /* Interface Description Block: linktype u16, reserved u16, snaplen u32 */
+            if (body_len >= 8 && !have_if0) {
+                snaplen0 = load32(file + body + 4, swapped);
+                have_if0 = 1;
+            }
+        } else if (type == 6u) { /* Enhanced Packet Block: interface, ts hi, ts lo, caplen, origlen, data */
+            if (body_len < 20) break;
+            const uint32_t caplen = load32(file + body + 12, swapped);
+            if (caplen > body_len - 20) break;
+            if (take_frame(l, file, body + 20, caplen, extract) != KMPB_OK) return KMPB_ENOMEM;
+        } else if (type == 2u) { /* obsolete Packet Block: interface u16, drops u16, ts hi, ts lo, caplen, len, data */
+            if (body_len < 20) break;
+            const uint32_t caplen = load32(file + body + 12, swapped);
+            if (caplen > body_len - 20) break;
+            if (take_frame(l, file, body + 20, caplen, extract) != KMPB_OK) return KMPB_ENOMEM;
+        } else if (type == 3u) { /* Simple Packet Block: origlen, data (captured = min(origlen, snaplen)) */
+            if (body_len < 4) break;
+            uint32_t caplen = load32(file + body, swapped);
+            if (have_if0 && snaplen0 && caplen > snaplen0) caplen = snaplen0;
+            if (caplen > body_len - 4) caplen = (uint32_t)(body_len - 4);
+            if (take_frame(l, file, body + 4, caplen, extract) != KMPB_OK) return KMPB_ENOMEM;
+        }
+        at += total;
+    }
     return KMPB_OK;
 }
 
@@ -149,20 +212,27 @@ int kmpb_pcap_open(const char *path, int proto, kmpb_pcap **out)
 
     uint32_t magic;
     memcpy(&magic, file, 4);
-    int swapped;
+    int swapped = 0, ng = 0;
     if (magic == 0xa1b2c3d4u || magic == 0xa1b23c4du) swapped = 0;        /* usec / nsec, host order */
     else if (magic == 0xd4c3b2a1u || magic == 0x4d3cb2a1u) swapped = 1;   /* written on the other endianness */
+    else if (magic == NG_SHB) ng = 1;                                     /* pcapng */
     else {
         munmap((void *)file, size);
         return kmpb_fail(KMPB_EFORMAT, "unknown file format");
     }
     extract_fn extract = proto == KMPB_PROTO_TCP ? kmpb_extract_tcp : kmpb_extract_udp;
     kmpb_pcap *pc = calloc(1, sizeof *pc);
-    if (pc == NULL || index_records(file, size, swapped, extract, &pc->refs, &pc->n_packets, &pc->n_frames, &pc->total_bytes) != KMPB_OK) {
+    ref_list list = {NULL, 0, 0, 0, 0};
+    if (pc == NULL || (ng ? index_pcapng(file, size, extract, &list) : index_classic(file, size, swapped, extract, &list)) != KMPB_OK) {
         free(pc);
+        free(list.refs);
         munmap((void *)file, size);
         return kmpb_fail(KMPB_ENOMEM, "out of memory indexing %s", path);
     }
+    pc->refs = list.refs;
+    pc->n_packets = list.packets;
+    pc->n_frames = list.frames;
+    pc->total_bytes = list.bytes;
     pc->file = file;
     pc->size = size;
     *out = pc;

@@ -147,6 +147,58 @@ def test_packer_savefile_variants(oracle, tmp_path):
     assert e.value.code == -5
 
 
+def _pcapng(frames, big_endian=False, simple_from=None, second_section_at=None):
+    """A pcapng file by hand: SHB, IDB, one packet block per frame (Enhanced; Simple from index `simple_from`
+    on), a name-resolution block in the middle, optionally a second section in the other byte order."""
+    import struct
+
+    def blocks(frames, e, first_index):
+        def block(btype, body):
+            body += b"\0" * (-len(body) % 4)
+            total = len(body) + 12
+            return struct.pack(e + "II", btype, total) + body + struct.pack(e + "I", total)
+
+        out = block(0x0A0D0D0A, struct.pack(e + "IHHq", 0x1A2B3C4D, 1, 0, -1) + struct.pack(e + "HH", 2, 5) + b"shark\0\0\0" + struct.pack(e + "HH", 0, 0))
+        out += block(1, struct.pack(e + "HHI", 1, 0, 262144))
+        for k, f in enumerate(frames):
+            if k == 1:
+                out += block(4, b"\0" * 8)  # a Name Resolution Block: skipped
+            if simple_from is not None and first_index + k >= simple_from:
+                out += block(3, struct.pack(e + "I", len(f)) + f)
+            else:
+                out += block(6, struct.pack(e + "IIIII", 0, 0, k, len(f), len(f)) + f + b"\0" * (-len(f) % 4) + struct.pack(e + "HHI", 1, 4, 0x64636261) + struct.pack(e + "HH", 0, 0))
+        return out
+
+    e = ">" if big_endian else "<"
+    if second_section_at is None:
+        return blocks(frames, e, 0)
+    other = "<" if big_endian else ">"
+    return blocks(frames[:second_section_at], e, 0) + blocks(frames[second_section_at:], other, second_section_at)
+
+
+def test_packer_reads_pcapng(tmp_path):
+    """libpcap also hands the reference pcapng files; same frames, same batch."""
+    frames = [_udp_frame(b"hello world"), b"short", _udp_frame(b"", ihl=6), _udp_frame(b"x" * 1401), _udp_frame(b"a\0b")]
+    classic = str(tmp_path / "classic.pcap")
+    _write_pcap(classic, frames)
+    b = kmp.PayloadBatch(classic, "udp")
+    want = (b.n_frames, b.offsets.tolist(), b.data.tobytes())
+    for name, kw in {"le": {}, "be": {"big_endian": True}, "simple": {"simple_from": 2},
+                     "two_sections": {"second_section_at": 3}, "two_sections_be": {"big_endian": True, "second_section_at": 2}}.items():
+        p = str(tmp_path / (name + ".pcapng"))
+        with open(p, "wb") as f:
+            f.write(_pcapng(frames, **kw))
+        b = kmp.PayloadBatch(p, "udp")
+        assert (b.n_frames, b.offsets.tolist(), b.data.tobytes()) == want, name
+    # a block cut short ends the walk silently
+    p = str(tmp_path / "cut.pcapng")
+    data = _pcapng(frames)
+    with open(p, "wb") as f:
+        f.write(data[:-30])
+    b = kmp.PayloadBatch(p, "udp")
+    assert (b.n_frames, b.n_packets) == (4, 3)
+
+
 def test_report_format(oracle):
     pats = [b"http", b"ack", b"zero", b"ack"]
     counts = [879, 8, 0, 8]
