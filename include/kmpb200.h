@@ -174,7 +174,7 @@ typedef struct kmpb_csr {
     int pinned;          /* 1: cudaHostAlloc memory, 0: malloc */
 } kmpb_csr;
 /* The pcap_open_offline / pcap_next_ex ingest loop, serial.c:91-141 (openmp_data.c:94-147): reads a
- * classic pcap savefile (either byte order, usec or nsec), extracts every frame's payload with the
+ * classic pcap savefile (either byte order, usec or nsec) or a pcapng file, extracts every frame's payload with the
  * chosen extractor over its captured length and packs the accepted payloads into a flat CSR batch,
  * in pinned memory when `pinned` is non-zero.  KMPB_EIO / KMPB_EFORMAT on failure. */
 int kmpb_load_pcap_csr(const char *path, int proto, int pinned, kmpb_csr *out);
