@@ -195,6 +195,19 @@ uint64_t kmpb_pcap_frames(const kmpb_pcap *pc);  /* records in the file */
 uint64_t kmpb_pcap_bytes(const kmpb_pcap *pc);   /* sum of the accepted payload lengths */
 int kmpb_count_pcap(kmpb_ctx *ctx, const kmpb_pcap *pc, uint64_t first, uint64_t count, uint64_t *counts_out);
 
+/* Frames arriving one at a time (live_openmp_task.c:160-217: pcap_next in a loop, batches handed to
+ * tasks while the capture goes on).  kmpb_stream_push runs the extractor on one captured frame and
+ * appends the accepted payload to the current batch in pinned memory; a full batch (batch_bytes, 0 =
+ * 8 MiB) is copied to the device and matched asynchronously while the caller keeps pushing.
+ * kmpb_stream_flush submits the partial batch, waits, and returns the counts accumulated since
+ * kmpb_stream_open in counts_out[n_pat]; pushing may continue afterwards.  One producer thread. */
+typedef struct kmpb_stream kmpb_stream;
+int kmpb_stream_open(kmpb_ctx *ctx, int proto, uint64_t batch_bytes, kmpb_stream **out);
+int kmpb_stream_push(kmpb_stream *st, const uint8_t *frame, uint32_t captured_len);
+int kmpb_stream_flush(kmpb_stream *st, uint64_t *counts_out);
+uint64_t kmpb_stream_packets(const kmpb_stream *st); /* payloads accepted so far */
+void kmpb_stream_close(kmpb_stream *st);
+
 /* The report, serial.c:163-168: header line, then "pattern: N times!" for every pattern with a
  * non-zero count, in pattern order.  Writes to `stream` (a FILE*, passed as void*). */
 int kmpb_print_report(void *stream, const kmpb_patterns *pats, const uint64_t *counts);

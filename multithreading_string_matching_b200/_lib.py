@@ -74,6 +74,11 @@ SIGNATURES = {
     "kmpb_pcap_frames": (ctypes.c_uint64, [ctypes.c_void_p]),
     "kmpb_pcap_bytes": (ctypes.c_uint64, [ctypes.c_void_p]),
     "kmpb_count_pcap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, c_u64p]),
+    "kmpb_stream_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),
+    "kmpb_stream_push": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32]),
+    "kmpb_stream_flush": (ctypes.c_int, [ctypes.c_void_p, c_u64p]),
+    "kmpb_stream_packets": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "kmpb_stream_close": (None, [ctypes.c_void_p]),
     "kmpb_print_report": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(CPatterns), c_u64p]),
     "kmpb_synth_bytes": (ctypes.c_uint64, [ctypes.POINTER(CSynth), ctypes.c_uint64, ctypes.c_uint64]),
     "kmpb_synth_fill_host": (ctypes.c_int, [ctypes.POINTER(CSynth), ctypes.c_uint64, ctypes.c_uint64,

@@ -458,6 +458,108 @@ int kmpb_count_pcap(kmpb_ctx *ctx, const kmpb_pcap *pc, uint64_t first, uint64_t
     return finish_chunked(ctx, n_slots, counts_out);
 }
 
+// ---- frames pushed one at a time (the live-capture shape) ----------------------------------------
+struct kmpb_stream {
+    kmpb_ctx *ctx;
+    int (*extract)(const uint8_t *, uint32_t, uint32_t *, uint32_t *);
+    uint64_t batch_bytes, max_pkts;
+    int slot;            // staging slot being filled
+    uint64_t n, bytes;   // packets and payload bytes in it
+    uint64_t batches, frames, packets;
+};
+
+static int stream_submit(kmpb_stream *st)
+{
+    kmpb_ctx *ctx = st->ctx;
+    if (st->n == 0) return KMPB_OK;
+    const int slot = st->slot;
+    cudaStream_t s = ctx->copy_stream[slot];
+    ctx->h_stage_off[slot][st->n] = st->bytes;
+    memset(ctx->h_stage_bytes[slot] + st->bytes, 0, 64);
+    KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_bytes[slot], ctx->h_stage_bytes[slot], st->bytes + 64, cudaMemcpyHostToDevice, s));
+    KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_off[slot], ctx->h_stage_off[slot], (st->n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    KMPB_CUDA(cudaEventRecord(ctx->ev_h2d[slot], s));
+    kmpb_batch b{ctx->d_stage_bytes[slot], 0, ctx->d_stage_off[slot], st->n, 0, st->bytes};
+    int rc = run_engine(ctx, b, slot, s); // accumulates into the slot's distinct-pattern counters
+    if (rc) return rc;
+    st->batches++;
+    st->slot = (slot + 1) % KMPB_COPY_STREAMS;
+    st->n = st->bytes = 0;
+    if (st->batches >= (uint64_t)KMPB_COPY_STREAMS) KMPB_CUDA(cudaEventSynchronize(ctx->ev_h2d[st->slot])); // its last copy has left it
+    return KMPB_OK;
+}
+
+int kmpb_stream_open(kmpb_ctx *ctx, int proto, uint64_t batch_bytes, kmpb_stream **out)
+{
+    if (ctx == nullptr || out == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL argument");
+    *out = nullptr;
+    if (!ctx->have_tables) return kmpb_fail(KMPB_ESTATE, "stream before kmpb_set_patterns");
+    if (proto != KMPB_PROTO_UDP && proto != KMPB_PROTO_TCP) return kmpb_fail(KMPB_EINVAL, "unknown protocol %d", proto);
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    if (batch_bytes == 0) batch_bytes = 8ull << 20;
+    if (batch_bytes < 65536) batch_bytes = 65536; // a frame's payload is at most 65535 - headers bytes long... jumbo included
+    const uint64_t max_pkts = 1ull << 20;
+    if ((rc = ensure_staging(ctx, batch_bytes, max_pkts))) return rc;
+    if ((rc = ensure_host_staging(ctx, batch_bytes, max_pkts))) return rc;
+    if ((rc = kmpb_union_scratch(ctx, batch_bytes))) return rc;
+    const uint32_t nu = ctx->host.n_uniq;
+    KMPB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    KMPB_CUDA(cudaMemsetAsync(ctx->d_uniq_counts, 0, (size_t)KMPB_COPY_STREAMS * (nu ? nu : 1) * sizeof(uint64_t), ctx->stream));
+    KMPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    kmpb_stream *st = new (std::nothrow) kmpb_stream();
+    if (st == nullptr) return kmpb_fail(KMPB_ENOMEM, "out of memory");
+    st->ctx = ctx;
+    st->extract = proto == KMPB_PROTO_TCP ? kmpb_extract_tcp : kmpb_extract_udp;
+    st->batch_bytes = batch_bytes;
+    st->max_pkts = max_pkts;
+    st->slot = 0;
+    st->n = st->bytes = st->batches = st->frames = st->packets = 0;
+    *out = st;
+    return KMPB_OK;
+}
+
+int kmpb_stream_push(kmpb_stream *st, const uint8_t *frame, uint32_t captured_len)
+{
+    if (st == nullptr || (frame == nullptr && captured_len)) return kmpb_fail(KMPB_EINVAL, "NULL argument");
+    uint32_t off = 0, len = 0;
+    st->frames++;
+    if (!st->extract(frame, captured_len, &off, &len)) return KMPB_OK;
+    if (len > st->batch_bytes) return kmpb_fail(KMPB_ELIMIT, "a %u-byte payload does not fit a %llu-byte batch", len, (unsigned long long)st->batch_bytes);
+    int rc = use_device(st->ctx);
+    if (rc) return rc;
+    if (st->bytes + len > st->batch_bytes || st->n == st->max_pkts)
+        if ((rc = stream_submit(st))) return rc;
+    kmpb_ctx *ctx = st->ctx;
+    ctx->h_stage_off[st->slot][st->n] = st->bytes;
+    memcpy(ctx->h_stage_bytes[st->slot] + st->bytes, frame + off, len);
+    st->n++;
+    st->bytes += len;
+    st->packets++;
+    return KMPB_OK;
+}
+
+int kmpb_stream_flush(kmpb_stream *st, uint64_t *counts_out)
+{
+    if (st == nullptr || counts_out == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL argument");
+    kmpb_ctx *ctx = st->ctx;
+    if (ctx->host.n_pat == 0) return KMPB_OK;
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    if ((rc = stream_submit(st))) return rc;
+    return finish_chunked(ctx, KMPB_COPY_STREAMS, counts_out);
+}
+
+uint64_t kmpb_stream_packets(const kmpb_stream *st) { return st ? st->packets : 0; }
+
+void kmpb_stream_close(kmpb_stream *st)
+{
+    if (st == nullptr) return;
+    cudaSetDevice(st->ctx->device);
+    cudaDeviceSynchronize();
+    delete st;
+}
+
 void *kmpb_host_alloc(size_t bytes)
 {
     void *p = nullptr;

@@ -210,6 +210,10 @@ class Matcher:
         finally:
             lib().kmpb_pcap_close(pc)
 
+    def stream(self, proto="udp", batch_bytes=0):
+        """Frames one at a time (the live_openmp_task.c shape): returns a FrameStream."""
+        return FrameStream(self, proto, batch_bytes)
+
     @property
     def launches(self):
         return lib().kmpb_launch_count(self._ctx)
@@ -226,6 +230,39 @@ class Matcher:
         out = (ctypes.c_double * 2)()
         check(lib().kmpb_last_timing(self._ctx, out, 2))
         return out[0], out[1]
+
+
+class FrameStream:
+    """kmpb_stream_*: push captured frames; batches are matched on the GPU while pushing goes on."""
+
+    def __init__(self, matcher, proto="udp", batch_bytes=0):
+        self._m = matcher
+        self._s = ctypes.c_void_p()
+        check(lib().kmpb_stream_open(matcher.handle, _PROTO[proto], batch_bytes, ctypes.byref(self._s)))
+
+    def push(self, frame):
+        frame = bytes(frame)
+        check(lib().kmpb_stream_push(self._s, frame, len(frame)))
+
+    def flush(self):
+        counts = np.zeros(max(len(self._m.patterns), 1), dtype=np.uint64)
+        check(lib().kmpb_stream_flush(self._s, counts.ctypes.data_as(c_u64p)))
+        return counts[: len(self._m.patterns)].tolist()
+
+    @property
+    def packets(self):
+        return lib().kmpb_stream_packets(self._s)
+
+    def close(self):
+        if self._s:
+            lib().kmpb_stream_close(self._s)
+            self._s = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class Synth:

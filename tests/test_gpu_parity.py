@@ -96,6 +96,38 @@ def test_streamed_path_chunks_and_slices(matchers, oracle, strings, tmp_path):
     assert m.count_pcap_streamed(path) == want
 
 
+def _classic_frames(path):
+    import struct
+    raw = open(path, "rb").read()
+    e = "<" if raw[:4] in (b"\xd4\xc3\xb2\xa1", b"\x4d\x3c\xb2\xa1") else ">"
+    at, out = 24, []
+    while at + 16 <= len(raw):
+        caplen = struct.unpack_from(e + "I", raw, at + 8)[0]
+        at += 16
+        if at + caplen > len(raw):
+            break
+        out.append(raw[at:at + caplen])
+        at += caplen
+    return out
+
+
+@pytest.mark.parametrize("pcap,proto,expected", golden_runs(), ids=lambda v: v if isinstance(v, str) else "")
+def test_frames_pushed_one_at_a_time(matchers, strings, pcap, proto, expected):
+    """kmpb_stream_*: the live-capture shape (live_openmp_task.c:160-217) fed with the frames of a savefile;
+    64 KB batches so that the staging slots are reused many times, a flush in the middle."""
+    m = matchers["union"]
+    m.set_patterns(strings)
+    frames = _classic_frames(os.path.join(DATA, pcap + ".pcap"))
+    with m.stream(proto, batch_bytes=65536) as st:
+        for f in frames[: len(frames) // 2]:
+            st.push(f)
+        st.flush()  # partial result; the stream goes on
+        for f in frames[len(frames) // 2:]:
+            st.push(f)
+        counts = st.flush()
+    assert kmp.format_report(strings, counts) == expected
+
+
 def test_cli_output_is_the_reference_output(strings):
     exe = os.path.join(ROOT, "multithreading_string_matching_b200", "bin", "kmp_match")
     for pcap, proto, expected in golden_runs():
