@@ -245,6 +245,18 @@ __device__ __forceinline__ void count_hit(const slow_ctx &c, uint32_t u)
     else atomicAdd(c.g_counts + u, 1ull);
 }
 
+// 4 text bytes starting at byte `pos` of the event at entry_sa, of which the first `need` (>= 1) matter: from
+// the event while its 36 bytes last, then from global memory (never past the word that holds the last
+// needed byte, which lies inside the packet)
+__device__ __forceinline__ uint32_t text_window(const slow_ctx &c, uint32_t entry_sa, uint32_t pos, uint32_t need)
+{
+    if (pos + 4 <= 36) return entry_window(entry_sa, pos);
+    const uint8_t *gw = c.bytes + (uint64_t)UN_GRP * lds32v(entry_sa + 36) + (pos & ~3u);
+    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(gw));
+    const uint32_t hi = (pos & 3u) + (need < 4 ? need : 4u) > 4u ? __ldg(reinterpret_cast<const uint32_t *>(gw) + 1) : 0u;
+    return __funnelshift_r(lo, hi, 8u * (pos & 3u));
+}
+
 // Every pattern that starts at byte `i` of the event at entry_sa and is at most `room` (>= 1) bytes long
 // is counted.  One loop over the key lengths that occur for this first byte, so that lanes probing
 // different tables still run the same instructions.
@@ -252,6 +264,9 @@ template <bool VS>
 __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_sa, uint32_t i, uint32_t room)
 {
     auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(c.vtab_sa + 4u * word) : __ldg(c.vtab_g + word); };
+    auto vt4 = [&](uint32_t word) -> uint4 {
+        return VS ? lds128v(c.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint4 *>(c.vtab_g + word));
+    };
     auto vt2 = [&](uint32_t word) -> uint2 {
         return VS ? lds64(c.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(c.vtab_g + word));
     };
@@ -262,6 +277,7 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_s
     lens &= (2u << (room < 4 ? room - 1 : 3)) - 1u;
     if (lens == 0) return;
     const uint32_t rec0 = vt(9), pat0 = vt(10);
+    const uint32_t x1 = room > 4 ? text_window(c, entry_sa, i + 4, room - 4) : 0u; // text bytes i+4..i+7
     do {
         const uint32_t L = __ffs(lens); // 1..4
         lens &= lens - 1;
@@ -277,28 +293,20 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_s
             }
         }
         while (u != 0xffffffffu) { // the patterns that share this key
-            const uint32_t m = vt(rec0 + 3 * u), pw0 = pat0 + vt(rec0 + 3 * u + 1), next = vt(rec0 + 3 * u + 2);
-            if (m <= room) { // else it would end past the packet (serial.c:191: the text ends there)
+            // record: {length | offset of the pattern's words << 8, pattern bytes 4..7, their mask, next}
+            const uint4 r = vt4(rec0 + 4 * u);
+            const uint32_t m = r.x & 0xffu;
+            // m <= room: else it would end past the packet (serial.c:191: the text ends there)
+            if (m <= room && ((x1 ^ r.y) & r.z) == 0) {
                 bool same = true;
-                for (uint32_t j = 4; j < m && same; j += 4) { // pattern bytes j..j+3 against text bytes i+j..
-                    const uint32_t pw = vt(pw0 + (j >> 2)), rem = m - j;
-                    // text bytes i+j..: from the event while they last (36 bytes), then from global memory
-                    const uint32_t pos = i + j;
-                    uint32_t t4;
-                    if (pos + 4 <= 36) {
-                        t4 = entry_window(entry_sa, pos);
-                    } else {
-                        const uint8_t *gw = c.bytes + (uint64_t)UN_GRP * lds32v(entry_sa + 36) + (pos & ~3u);
-                        const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(gw));
-                        const uint32_t hi = (pos & 3u) + (rem < 4 ? rem : 4u) > 4u ? __ldg(reinterpret_cast<const uint32_t *>(gw) + 1) : 0u;
-                        t4 = __funnelshift_r(lo, hi, 8u * (pos & 3u));
-                    }
-                    const uint32_t diff = t4 ^ pw;
+                for (uint32_t j = 8; j < m && same; j += 4) { // pattern bytes j..j+3 against text bytes i+j..
+                    const uint32_t pw = vt(pat0 + (r.x >> 8) + (j >> 2)), rem = m - j;
+                    const uint32_t diff = text_window(c, entry_sa, i + j, rem) ^ pw;
                     same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
                 }
                 if (same) count_hit(c, u);
             }
-            u = next;
+            u = r.w;
         }
     } while (lens);
 }

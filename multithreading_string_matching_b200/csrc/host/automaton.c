@@ -395,8 +395,9 @@ static int build_verify_tables(kmpb_tables *t)
         toff[L] = at;
         at += 2 * n;
     }
+    at = (at + 3u) & ~3u; /* records are read 16 bytes at a time */
     const uint32_t rec_off = at;
-    at += 3 * t->n_uniq;
+    at += 4 * t->n_uniq;
     const uint32_t blob_off = at;
     at += blob_words;
     uint32_t *v = calloc(at ? at : 1, sizeof *v);
@@ -414,10 +415,14 @@ static int build_verify_tables(kmpb_tables *t)
     for (uint32_t u = 0; u < t->n_uniq; u++) {
         const uint8_t *p = t->uniq_blob + t->uniq_off[u];
         const uint32_t len = t->uniq_len[u], L = len < 4 ? len : 4, key = key_of(p, len);
-        uint32_t *rec = v + rec_off + 3 * u;
-        rec[0] = len;
-        rec[1] = bw;
-        rec[2] = VT_EMPTY;
+        uint32_t *rec = v + rec_off + 4 * u;
+        rec[0] = len | bw << 8;
+        rec[1] = rec[2] = 0; /* pattern bytes 4..7 and the mask of those that exist */
+        for (uint32_t i = 4; i < 8 && i < len; i++) {
+            rec[1] |= (uint32_t)p[i] << (8 * (i - 4));
+            rec[2] |= 0xffu << (8 * (i - 4));
+        }
+        rec[3] = VT_EMPTY;
         memcpy((uint8_t *)(v + blob_off + bw), p, len); /* rest of the last word stays zero */
         bw += (len + 3) / 4;
         /* which key lengths can start with these two bytes (a 1-byte pattern: any second byte) */
@@ -433,7 +438,7 @@ static int build_verify_tables(kmpb_tables *t)
                 break;
             }
             if (slot[0] == key) {
-                rec[2] = slot[1]; /* push front */
+                rec[3] = slot[1]; /* push front */
                 slot[1] = u;
                 break;
             }

@@ -58,7 +58,8 @@ typedef struct kmpb_tables {
      *   [12..267] 1024 bytes: byte kmpb_vtab_lens_slot(first two text bytes) has bit L-1 set when some pattern with
      *            key length L starts with those two bytes (a 1-byte pattern: with that byte)
      *   tables: slots of 2 words {key, first record or 0xffffffff}
-     *   records (3 words per distinct pattern): {length, word offset of its bytes inside the pattern words,
+     *   records (4 words per distinct pattern, 16-byte aligned): {length | word offset of its bytes inside the
+     *            pattern words << 8, pattern bytes 4..7 (zero padded), mask of those bytes that exist,
      *            next record with the same 4-byte key or 0xffffffff}
      *   pattern words: every pattern zero-padded to a multiple of 4 bytes */
     uint32_t *vtab;

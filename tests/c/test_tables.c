@@ -90,9 +90,13 @@ static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int
                     const uint32_t *e = v + v[L] + 2 * slot;
                     if (e[1] == 0xffffffffu) break;
                     if (e[0] != key) continue;
-                    for (uint32_t u = e[1]; u != 0xffffffffu; u = v[v[9] + 3 * u + 2]) {
-                        const uint32_t len = v[v[9] + 3 * u];
-                        const uint8_t *pb = (const uint8_t *)(v + v[10] + v[v[9] + 3 * u + 1]);
+                    for (uint32_t u = e[1]; u != 0xffffffffu; u = v[v[9] + 4 * u + 3]) {
+                        const uint32_t len = v[v[9] + 4 * u] & 0xffu;
+                        const uint8_t *pb = (const uint8_t *)(v + v[10] + (v[v[9] + 4 * u] >> 8));
+                        uint32_t x1 = 0; /* the inlined second word agrees with the pattern bytes */
+                        for (uint32_t k = 4; k < 8 && k < len; k++) x1 |= (uint32_t)pb[k] << (8 * (k - 4));
+                        if (x1 != v[v[9] + 4 * u + 1] || (len > 4 && v[v[9] + 4 * u + 2] != (len >= 8 ? 0xffffffffu : (1u << (8 * (len - 4))) - 1u))
+                            || (len <= 4 && v[v[9] + 4 * u + 2] != 0)) { fprintf(stderr, "record %u: inlined word wrong\n", u); bad = 1; }
                         if (s + (int)len <= text_len && memcmp(text + s, pb, len) == 0) got_hash[u]++;
                     }
                     break;
