@@ -128,6 +128,19 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_sa, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa), "l"(src) : "memory");
 }
+// pointer + 32-bit offset as IMAD.WIDE.U32 (FMA pipe), not IADD3 + IADD3.X (ALU pipe)
+__device__ __forceinline__ const uint8_t *add_wide(const uint8_t *base, uint32_t offset)
+{
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(offset), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<const uint8_t *>(r);
+}
+// the same under a predicate (no branch around a single copy)
+__device__ __forceinline__ void cp_async16_if(bool on, uint32_t dst_sa, const void *src)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p cp.async.cg.shared.global [%1], [%2], 16;\n\t}"
+                 ::"r"((uint32_t)on), "r"(dst_sa), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait()
@@ -551,14 +564,15 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         auto issue_row = [&](uint32_t r, uint32_t slot) {
             const uint32_t row = r * UN_ROW, g = row + lane * UN_GRP;
             const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES;
+            const uint8_t *src = add_wide(text, g); // one multiply-add on the FMA pipe instead of two ALU adds
             if (row + UN_SLOT_BYTES <= load_end) {
-                cp_async16(dst + off0, text + g);
-                cp_async16(dst + off1, text + g + 16);
-                if (lane == 31) cp_async16(dst + offtail, text + g + 32);
+                cp_async16(dst + off0, src);
+                cp_async16(dst + off1, src + 16);
+                cp_async16_if(lane == 31, dst + offtail, src + 32);
             } else if (r < nrows) {
-                if (g < load_end) cp_async16(dst + off0, text + g);
-                if (g + 16 < load_end) cp_async16(dst + off1, text + g + 16);
-                if (lane == 31 && g + 32 < load_end) cp_async16(dst + offtail, text + g + 32);
+                if (g < load_end) cp_async16(dst + off0, src);
+                if (g + 16 < load_end) cp_async16(dst + off1, src + 16);
+                if (lane == 31 && g + 32 < load_end) cp_async16(dst + offtail, src + 32);
             }
             cp_async_commit();
         };
