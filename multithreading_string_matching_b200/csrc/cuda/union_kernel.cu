@@ -61,6 +61,10 @@ constexpr uint32_t UN_ROW = 32 * UN_GRP;                  // bytes per warp row
 constexpr uint32_t UN_SLOTS = KMPB_UN_SLOTS;              // rows in flight per warp (cp.async -> shared memory)
 constexpr uint32_t UN_SLOT_BYTES = UN_ROW + 16;           // a row and the 16 bytes after it (lookahead)
 constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item size
+#ifndef KMPB_UN_TAIL_ITEMS
+#define KMPB_UN_TAIL_ITEMS 16384
+#endif
+constexpr uint32_t UN_TAIL_ITEMS = KMPB_UN_TAIL_ITEMS;   // quarter-size items at the end of a batch (about one per warp x 4)
 constexpr uint32_t UN_QCAP = 32;                          // events per warp list
 constexpr uint32_t UN_Q_WORDS = 12; // event: 32 B group, 4 B lookahead, group index, quarter reports, item (48 B)
 constexpr uint32_t UN_LUT_BYTES = 256 * 256; // 256-byte row per byte value; lanes use the first 128 B
@@ -105,15 +109,17 @@ struct union_params {
 
 // ---- work partition: item i = packets [items[i], items[i+1]) ---------------------------------
 __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets, uint32_t n_packets,
-                                            uint32_t n_items, uint64_t item_bytes, uint32_t *__restrict__ items,
+                                            uint32_t n_items, uint32_t n_big, uint64_t item_bytes, uint32_t *__restrict__ items,
                                             uint32_t *__restrict__ work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { work[0] = 0; work[1] = 0; work[2] = 0; }
     if (i > n_items) return;
     if (i == n_items) { items[i] = n_packets; return; }
-    // first packet whose start is >= offsets[0] + i * item_bytes
-    const uint64_t target = offsets[0] + (uint64_t)i * item_bytes;
+    // first packet whose start is >= the item's target byte: n_big items of item_bytes, then quarter-size
+    // items, so that the warps run dry within a quarter item of each other at the end of the batch
+    const uint64_t target = offsets[0] + (i <= n_big ? (uint64_t)i * item_bytes
+                                                     : (uint64_t)n_big * item_bytes + (uint64_t)(i - n_big) * (item_bytes / 4));
     uint32_t lo = 0, hi = n_packets;
     while (lo < hi) {
         uint32_t mid = lo + (hi - lo) / 2;
@@ -695,7 +701,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
 // scratch for batches of up to max_batch_bytes: work counters and the item table, one set per slot
 int kmpb_union_scratch(kmpb_ctx *ctx, uint64_t max_batch_bytes)
 {
-    size_t need = (size_t)(max_batch_bytes / UN_ITEM_BYTES) + 3;
+    size_t need = (size_t)(max_batch_bytes / UN_ITEM_BYTES) + UN_TAIL_ITEMS + 8;
     if (need <= ctx->items_cap && ctx->d_items && ctx->d_work) return KMPB_OK;
     cudaFree(ctx->d_items);
     ctx->d_items = nullptr;
@@ -717,7 +723,11 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     if (b.end_byte - b.abs_base >= (1ull << 36))
         return kmpb_fail(KMPB_ELIMIT, "more than 64 GiB of payload in one batch");
     const uint64_t span = b.end_byte - b.first_byte;
-    const uint32_t n_items = (uint32_t)((span + UN_ITEM_BYTES - 1) / UN_ITEM_BYTES);
+    // full-size items, except the last UN_TAIL_ITEMS/4 items' worth of bytes, which is cut into quarter-size items
+    const uint64_t whole = span / UN_ITEM_BYTES;
+    const uint32_t n_big = (uint32_t)(whole > UN_TAIL_ITEMS / 4 ? whole - UN_TAIL_ITEMS / 4 : 0);
+    const uint64_t small_span = span - (uint64_t)n_big * UN_ITEM_BYTES;
+    const uint32_t n_items = n_big + (uint32_t)((small_span + UN_ITEM_BYTES / 4 - 1) / (UN_ITEM_BYTES / 4));
     if ((size_t)n_items + 1 > ctx->items_cap) return kmpb_fail(KMPB_ESTATE, "union scratch too small");
     uint32_t *d_items = ctx->d_items + (size_t)slot * ctx->items_cap;
     uint32_t *d_work = ctx->d_work + slot * 4;
@@ -734,7 +744,7 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
         ctx->attr_union_set = true;
     }
     kmpb_union_partition_kernel<<<(n_items + 1 + 255) / 256, 256, 0, stream>>>(b.d_offsets, (uint32_t)b.n_packets, n_items,
-                                                                              UN_ITEM_BYTES, d_items, d_work);
+                                                                              n_big, UN_ITEM_BYTES, d_items, d_work);
     union_params p;
     p.bytes = b.d_bytes;
     p.abs_base = b.abs_base;
