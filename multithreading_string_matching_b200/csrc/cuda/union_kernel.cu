@@ -723,9 +723,11 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     if (b.end_byte - b.abs_base >= (1ull << 36))
         return kmpb_fail(KMPB_ELIMIT, "more than 64 GiB of payload in one batch");
     const uint64_t span = b.end_byte - b.first_byte;
-    // full-size items, except the last UN_TAIL_ITEMS/4 items' worth of bytes, which is cut into quarter-size items
+    // full-size items, except the last UN_TAIL_ITEMS/4 items' worth of bytes (at most an eighth of the batch),
+    // which is cut into quarter-size items
     const uint64_t whole = span / UN_ITEM_BYTES;
-    const uint32_t n_big = (uint32_t)(whole > UN_TAIL_ITEMS / 4 ? whole - UN_TAIL_ITEMS / 4 : 0);
+    const uint64_t tail_items = std::min<uint64_t>(UN_TAIL_ITEMS / 4, whole / 8); // at most an eighth of the batch
+    const uint32_t n_big = (uint32_t)(whole - tail_items);
     const uint64_t small_span = span - (uint64_t)n_big * UN_ITEM_BYTES;
     const uint32_t n_items = n_big + (uint32_t)((small_span + UN_ITEM_BYTES / 4 - 1) / (UN_ITEM_BYTES / 4));
     if ((size_t)n_items + 1 > ctx->items_cap) return kmpb_fail(KMPB_ESTATE, "union scratch too small");
