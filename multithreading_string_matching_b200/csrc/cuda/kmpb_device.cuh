@@ -29,13 +29,7 @@ struct kmpb_device_tables {
     int32_t *pi = nullptr;          // [sum len], pattern u at uniq_off[u]
     uint8_t *perpat_dfa = nullptr;  // pattern u: uniq_len[u] rows of 256 entries at 256*uniq_off[u]
     // union engine
-    uint32_t *next = nullptr;       // [n_state*n_class]
-    uint32_t *trie = nullptr;       // [n_state*n_class]
-    uint32_t *state_term = nullptr; // [n_state]
     uint32_t *vtab = nullptr;       // [vtab_words] start-anchored verification tables (automaton.c)
-    uint32_t *out_head = nullptr;   // [n_state+1]
-    uint32_t *out_id = nullptr;
-    uint8_t *byte_class = nullptr;  // [256]
     uint32_t *filter = nullptr;     // [256]
 };
 

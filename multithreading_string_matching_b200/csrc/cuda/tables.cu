@@ -2,8 +2,9 @@
 //
 // The KMP failure tables (kmp_prefix, serial.c:217-238) are built ON THE DEVICE, one thread per
 // distinct pattern, and expanded on the device into byte-indexed transition DFAs (one row of 256
-// entries per state) for the per-pattern engine.  The union automaton and the prefilter come from
-// csrc/host/automaton.c and are uploaded here.
+// entries per state) for the per-pattern engine.  The union engine's prefilter and start-anchored hash
+// tables come from csrc/host/automaton.c and are uploaded here (the merged automaton itself stays on the
+// host, where tests/c/test_tables.c checks the tables against it).
 #include <stdlib.h>
 #include <string.h>
 
@@ -60,8 +61,7 @@ void kmpb_release_tables(kmpb_ctx *ctx)
 {
     kmpb_device_tables &d = ctx->dev;
     cudaFree(d.uniq_blob); cudaFree(d.uniq_off); cudaFree(d.uniq_len); cudaFree(d.pat_to_uniq);
-    cudaFree(d.pi); cudaFree(d.perpat_dfa); cudaFree(d.next); cudaFree(d.out_head); cudaFree(d.out_id);
-    cudaFree(d.byte_class); cudaFree(d.filter); cudaFree(d.trie); cudaFree(d.state_term); cudaFree(d.vtab);
+    cudaFree(d.pi); cudaFree(d.perpat_dfa); cudaFree(d.filter); cudaFree(d.vtab);
     d = kmpb_device_tables();
     cudaFree(ctx->d_uniq_counts); ctx->d_uniq_counts = nullptr;
     cudaFree(ctx->d_counts); ctx->d_counts = nullptr;
@@ -82,13 +82,7 @@ int kmpb_upload_tables(kmpb_ctx *ctx)
     if ((rc = upload(&d.uniq_off, h.uniq_off, (size_t)h.n_uniq + 1, s))) return rc;
     if ((rc = upload(&d.uniq_len, h.uniq_len, h.n_uniq, s))) return rc;
     if ((rc = upload(&d.pat_to_uniq, h.pat_to_uniq, h.n_pat, s))) return rc;
-    if ((rc = upload(&d.next, h.next, (size_t)h.n_state * h.n_class, s))) return rc;
-    if ((rc = upload(&d.trie, h.trie, (size_t)h.n_state * h.n_class, s))) return rc;
-    if ((rc = upload(&d.state_term, h.state_term, (size_t)h.n_state, s))) return rc;
     if ((rc = upload(&d.vtab, h.vtab, (size_t)h.vtab_words, s))) return rc;
-    if ((rc = upload(&d.out_head, h.out_head, (size_t)h.n_state + 1, s))) return rc;
-    if ((rc = upload(&d.out_id, h.out_id, (size_t)h.out_head[h.n_state], s))) return rc;
-    if ((rc = upload(&d.byte_class, h.byte_class, 256, s))) return rc;
     if ((rc = upload(&d.filter, h.filter, 256, s))) return rc;
     KMPB_CUDA(cudaMalloc((void **)&d.pi, (blob_len ? blob_len : 1) * sizeof(int32_t)));
     KMPB_CUDA(cudaMalloc((void **)&d.perpat_dfa, blob_len ? blob_len * 256 : 1));
