@@ -66,7 +66,7 @@ constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item si
 #endif
 constexpr uint32_t UN_TAIL_ITEMS = KMPB_UN_TAIL_ITEMS;   // quarter-size items at the end of a batch (about one per warp x 4)
 constexpr uint32_t UN_QCAP = 32;                          // events per warp list
-constexpr uint32_t UN_Q_WORDS = 12; // event: 32 B group, 4 B lookahead, group index, quarter reports, item (48 B)
+constexpr uint32_t UN_Q_WORDS = 12; // event: 32 B group, 8 B lookahead, group index | item parity << 31, quarter reports (48 B)
 constexpr uint32_t UN_LUT_BYTES = 256 * 256; // 256-byte row per byte value; lanes use the first 128 B
 constexpr uint32_t FULL = 0xffffffffu;
 
@@ -75,7 +75,7 @@ constexpr uint32_t FULL = 0xffffffffu;
 // the per-warp row rings follow the LUT, the verification tables follow the rings (as long as they fit).
 constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_WORDS * 4;
 constexpr uint32_t UN_RING_BYTES = UN_WARPS * UN_SLOTS * UN_SLOT_BYTES;
-constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
+constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 256;
 constexpr uint32_t UN_FRONT_FIXED = UN_Q_BYTES + UN_SCRATCH_BYTES + 16;
 constexpr uint32_t UN_FRONT_MAX = 60 * 1024; // what the gap is trusted to hold
 constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_RING_BYTES;
@@ -97,6 +97,7 @@ struct union_params {
     uint32_t vtab_in_smem;   // the hash verification tables live in shared memory
     const uint32_t *vtab;    // hash verification tables (automaton.c build_verify_tables)
     uint32_t vtab_words;
+    uint32_t vtab_one_off;   // vtab[5]: the one-byte patterns' table, 0 = none
     uint32_t mul256; // the value 256, passed at run time so the shift-or-0xff compiles to an integer
                      // multiply-add on the FMA pipe instead of competing for the ALU pipe
     unsigned long long *uniq_counts;
@@ -178,6 +179,12 @@ __device__ __forceinline__ uint2 lds64(uint32_t saddr)
     asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ uint2 lds64v(uint32_t saddr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t lds32v(uint32_t saddr)
 {
     uint32_t v;
@@ -188,7 +195,7 @@ __device__ __forceinline__ void sts128v(uint32_t saddr, uint32_t a, uint32_t b, 
 {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// 4 text bytes starting at byte `pos` of an event (pos + 4 <= 36)
+// 4 text bytes starting at byte `pos` of an event (pos + 4 <= 40)
 __device__ __forceinline__ uint32_t entry_window(uint32_t entry_sa, uint32_t pos)
 {
     const uint32_t a = entry_sa + (pos & ~3u);
@@ -249,85 +256,83 @@ struct slow_ctx {
     const uint8_t *bytes; // absolute byte abs_base
     uint64_t abs_base;
     const uint64_t *offsets;
-    const uint32_t *items;
     const uint32_t *vtab_g; // verification tables in global memory
     uint32_t vtab_sa;       // ... or their shared address (vtab_in_smem)
     uint32_t vtab_in_smem;
-    uint32_t scratch_sa;    // 32 words of per-warp scratch
-    uint32_t *s_counts;     // shared counters, or nullptr
+    uint32_t one_off;       // word offset of the one-byte patterns' table, 0 = none
+    uint32_t scratch_sa;    // per-warp scratch: {ks, ke, b_abs, e_abs} of the items of either parity (2 x 32 B),
+                            // 32 words the resolve step publishes, item parity and the "previous item pending" flag
+    uint32_t s_counts_sa;   // shared address of the shared counters, or 0
     unsigned long long *g_counts;
 };
 
-__device__ __forceinline__ void count_hit(const slow_ctx &c, uint32_t u)
+// the hot fields of slow_ctx, read once per resolve step (the context itself lives in local memory)
+struct verify_ctx {
+    uint32_t vtab_sa, one_off, s_counts_sa;
+};
+
+__device__ __forceinline__ void count_hit(const slow_ctx &c, const verify_ctx &v, uint32_t u)
 {
-    if (c.s_counts) atomicAdd(&c.s_counts[u], 1u);
+    if (v.s_counts_sa) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(v.s_counts_sa + 4u * u) : "memory");
     else atomicAdd(c.g_counts + u, 1ull);
 }
 
 // 4 text bytes starting at byte `pos` of the event at entry_sa, of which the first `need` (>= 1) matter: from
-// the event while its 36 bytes last, then from global memory (never past the word that holds the last
+// the event while its 40 bytes last, then from global memory (never past the word that holds the last
 // needed byte, which lies inside the packet)
 __device__ __forceinline__ uint32_t text_window(const slow_ctx &c, uint32_t entry_sa, uint32_t pos, uint32_t need)
 {
-    if (pos + 4 <= 36) return entry_window(entry_sa, pos);
-    const uint8_t *gw = c.bytes + (uint64_t)UN_GRP * lds32v(entry_sa + 36) + (pos & ~3u);
+    if (pos + 4 <= 40) return entry_window(entry_sa, pos);
+    const uint8_t *gw = c.bytes + (uint64_t)UN_GRP * (lds32v(entry_sa + 40) & 0x7fffffffu) + (pos & ~3u);
     const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(gw));
     const uint32_t hi = (pos & 3u) + (need < 4 ? need : 4u) > 4u ? __ldg(reinterpret_cast<const uint32_t *>(gw) + 1) : 0u;
     return __funnelshift_r(lo, hi, 8u * (pos & 3u));
 }
 
 // Every pattern that starts at byte `i` of the event at entry_sa and is at most `room` (>= 1) bytes long
-// is counted.  One loop over the key lengths that occur for this first byte, so that lanes probing
-// different tables still run the same instructions.
+// is counted.  The candidate's first two bytes select one slot of the verification tables (automaton.c
+// build_verify_tables); the slot's records -- the patterns whose first two bytes hash there, usually those of one
+// two-byte prefix -- carry the pattern's first 8 bytes and their masks, so a record costs one 16-byte load and one
+// masked compare, and only a record that agrees on those bytes is looked at further.
 template <bool VS>
-__device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_sa, uint32_t i, uint32_t room)
+__device__ __forceinline__ void verify_start(const slow_ctx &c, const verify_ctx &v, const uint4 hdr, uint32_t entry_sa, uint32_t i,
+                                             uint32_t room)
 {
-    auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(c.vtab_sa + 4u * word) : __ldg(c.vtab_g + word); };
+    auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(v.vtab_sa + 4u * word) : __ldg(c.vtab_g + word); };
     auto vt4 = [&](uint32_t word) -> uint4 {
-        return VS ? lds128v(c.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint4 *>(c.vtab_g + word));
+        return VS ? lds128v(v.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint4 *>(c.vtab_g + word));
     };
     auto vt2 = [&](uint32_t word) -> uint2 {
-        return VS ? lds64(c.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(c.vtab_g + word));
+        return VS ? lds64(v.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(c.vtab_g + word));
     };
+    // hdr = vtab[1..4]: slots, hash shift, records, pattern words
     const uint32_t x0 = entry_window(entry_sa, i);
-    // key lengths of the patterns that can start with these two bytes, cut to what fits before the packet ends
-    const uint32_t ls = ((x0 & 0xffffu) * 0x9e3779b1u) >> 22;
-    uint32_t lens = VS ? lds8v(c.vtab_sa + 48u + ls) : (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(c.vtab_g + 12) + ls);
-    lens &= (2u << (room < 4 ? room - 1 : 3)) - 1u;
-    if (lens == 0) return;
-    const uint32_t rec0 = vt(9), pat0 = vt(10);
+    if (v.one_off) { // one-byte patterns: a direct table (room >= 1 always holds)
+        const uint32_t u = vt(v.one_off + (x0 & 0xffu));
+        if (u != 0xffffffffu) count_hit(c, v, u);
+    }
+    const uint2 e = vt2(hdr.x + 2u * (((x0 & 0xffffu) * 0x9e3779b1u) >> hdr.y)); // {first record, records}
+    if (e.y == 0 || room < 2) return;
     const uint32_t x1 = room > 4 ? text_window(c, entry_sa, i + 4, room - 4) : 0u; // text bytes i+4..i+7
-    do {
-        const uint32_t L = __ffs(lens); // 1..4
-        lens &= lens - 1;
-        const uint32_t key = x0 & (0xffffffffu >> (32u - 8u * L));
-        const uint32_t mask = vt(4 + L), tab0 = vt(L);
-        uint32_t u = 0xffffffffu;
-        for (uint32_t slot = ((key * 0x9e3779b1u) >> 12) & mask;; slot = (slot + 1) & mask) {
-            const uint2 e = vt2(tab0 + 2 * slot);
-            if (e.y == 0xffffffffu) break;
-            if (e.x == key) {
-                u = e.y;
-                break;
+    for (uint32_t r = hdr.z + 8u * e.x, rend = r + 8u * e.y; r != rend; r += 8) {
+        const uint4 a = vt4(r); // pattern bytes 0..3, their mask, bytes 4..7, their mask
+        if ((((x0 ^ a.x) & a.y) | ((x1 ^ a.z) & a.w)) != 0) continue;
+        const uint2 b = vt2(r + 4); // length, distinct id
+        const uint32_t m = b.x;
+        // m <= room: else it would end past the packet (serial.c:191: the text ends there); the bytes of x0/x1 past
+        // `room` are not text of this packet, but a pattern that short compares none of them
+        if (m > room) continue;
+        bool same = true;
+        if (m > 8) {
+            const uint32_t pw0 = hdr.w + vt(r + 6);
+            for (uint32_t j = 8; j < m && same; j += 4) { // pattern bytes j..j+3 against text bytes i+j..
+                const uint32_t pw = vt(pw0 + (j >> 2)), rem = m - j;
+                const uint32_t diff = text_window(c, entry_sa, i + j, rem) ^ pw;
+                same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
             }
         }
-        while (u != 0xffffffffu) { // the patterns that share this key
-            // record: {length | offset of the pattern's words << 8, pattern bytes 4..7, their mask, next}
-            const uint4 r = vt4(rec0 + 4 * u);
-            const uint32_t m = r.x & 0xffu;
-            // m <= room: else it would end past the packet (serial.c:191: the text ends there)
-            if (m <= room && ((x1 ^ r.y) & r.z) == 0) {
-                bool same = true;
-                for (uint32_t j = 8; j < m && same; j += 4) { // pattern bytes j..j+3 against text bytes i+j..
-                    const uint32_t pw = vt(pat0 + (r.x >> 8) + (j >> 2)), rem = m - j;
-                    const uint32_t diff = text_window(c, entry_sa, i + j, rem) ^ pw;
-                    same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
-                }
-                if (same) count_hit(c, u);
-            }
-            u = r.w;
-        }
-    } while (lens);
+        if (same) count_hit(c, v, b.y);
+    }
 }
 
 // Resolve the warp's n pending events (n <= 32).  carry = 1 + absolute position of the last NUL byte
@@ -337,6 +342,12 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, uint32_t entry_s
 // group lies in -> mask of candidate starts that are alive (inside the item, no NUL before them in their
 // packet) and mask of packet boundaries inside the group.
 // Phase 2, one alive candidate per lane, whichever event it came from: hash lookup and count.
+//
+//
+// The pending events belong to the work item the warp is scanning or to the one before it (the row loop sees to
+// that); an event carries its item's parity, and the packets [ks, ke) and bytes [b_abs, e_abs) of both items wait in
+// the warp's scratch words, where the warp put them when it took the item: no lane has to look them up in global
+// memory, and the row loop does not keep them in registers.
 __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t q_sa, const uint32_t n, uint64_t carry,
                                               const uint32_t lutlane, const uint32_t mul)
 {
@@ -347,16 +358,19 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
     uint64_t gq = 0, b_abs = 0, e_abs = 0; // my group's first byte; my item's byte range (absolute)
     uint32_t ks = 0, ke = 0;
     if (lane < n) {
-        const uint4 t = lds128v(entry_sa + 32); // lookahead, group index, quarter reports, item
-        gq = c.abs_base + (uint64_t)UN_GRP * t.y;
-        ks = __ldg(c.items + t.w);
-        ke = __ldg(c.items + t.w + 1);
-        b_abs = __ldg(c.offsets + ks);
-        e_abs = __ldg(c.offsets + ke);
+        const uint2 t = lds64v(entry_sa + 40); // group index | item parity << 31, quarter reports
+        gq = c.abs_base + (uint64_t)UN_GRP * (t.x & 0x7fffffffu);
+        const uint32_t set_sa = c.scratch_sa + ((t.x >> 31) << 5); // my item's {ks, ke, b_abs, e_abs}
+        const uint4 iw = lds128v(set_sa);
+        const uint2 iw2 = lds64v(set_sa + 16);
+        ks = iw.x;
+        ke = iw.y;
+        b_abs = (uint64_t)iw.w << 32 | iw.z;
+        e_abs = (uint64_t)iw2.y << 32 | iw2.x;
         // Re-run the filter over the quarters that reported, this time recording which start positions
         // fired and which bytes are NUL.  Quarter k: bytes 8k..8k+10 (three bytes of run-in, then starts
         // 8k..8k+7 report at bytes 8k+3..8k+10); the NUL bit is exact from the first byte on.
-        uint32_t quarters = ((((t.z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t.z) & 0x80808080u); // bit 8k+7: quarter k
+        uint32_t quarters = ((((t.y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t.y) & 0x80808080u); // bit 8k+7: quarter k
         while (quarters) {
             const uint32_t k8 = (__ffs(quarters) - 1) & ~7u; // 8k
             quarters &= quarters - 1;
@@ -431,7 +445,8 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
     }
     // publish what phase 2 needs next to the event's bytes
     if (lane < n) {
-        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(entry_sa + 40), "r"(bm), "r"(nextb) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(entry_sa + 44), "r"(bm) : "memory"); // over the quarter reports
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.scratch_sa + 64 + 4 * lane), "r"(nextb) : "memory");
     }
     // alive candidates, numbered across the lanes
     const uint32_t cnt = __popc(am);
@@ -444,6 +459,14 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
     const uint32_t total = __shfl_sync(FULL, incl, 31);
     const uint32_t excl = incl - cnt;
     __syncwarp();
+    verify_ctx vc;
+    vc.vtab_sa = c.vtab_sa;
+    vc.one_off = c.one_off;
+    vc.s_counts_sa = c.s_counts_sa;
+    // vtab[1..4]: where the slots, the records and the pattern words are
+    const uint4 vhdr = total == 0 ? make_uint4(0, 0, 0, 0)
+                       : c.vtab_in_smem ? make_uint4(lds32(c.vtab_sa + 4), lds32(c.vtab_sa + 8), lds32(c.vtab_sa + 12), lds32(c.vtab_sa + 16))
+                                        : make_uint4(__ldg(c.vtab_g + 1), __ldg(c.vtab_g + 2), __ldg(c.vtab_g + 3), __ldg(c.vtab_g + 4));
     for (uint32_t t0 = 0; t0 < total; t0 += 32) {
         const uint32_t t = t0 + lane;
         // owner of candidate t: the first lane whose inclusive count exceeds t
@@ -460,12 +483,11 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
             for (uint32_t j = first; j < t; j++) m &= m - 1;
             const uint32_t i = __ffs(m) - 1;
             const uint32_t owner_sa = q_sa + l * (UN_Q_WORDS * 4);
-            uint32_t obm, onext;
-            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(obm), "=r"(onext) : "r"(owner_sa + 40) : "memory");
+            const uint32_t obm = lds32v(owner_sa + 44), onext = lds32v(c.scratch_sa + 64 + 4 * l);
             const uint32_t above = obm & ~((2u << i) - 1u); // packet starts after byte i
             const uint32_t room = (above ? (uint32_t)__ffs(above) - 1u : onext) - i;
-            if (c.vtab_in_smem) verify_start<true>(c, owner_sa, i, room);
-            else verify_start<false>(c, owner_sa, i, room);
+            if (c.vtab_in_smem) verify_start<true>(c, vc, vhdr, owner_sa, i, room);
+            else verify_start<false>(c, vc, vhdr, owner_sa, i, room);
         }
     }
     __syncwarp();
@@ -506,6 +528,10 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     if (p.vtab_in_smem)
         for (uint32_t i = threadIdx.x; i < p.vtab_words; i += UN_THREADS) s_vtab[i] = p.vtab[i];
     if (threadIdx.x == 0) *s_lut_saddr = dyn_saddr + lut_off;
+    if (threadIdx.x < UN_WARPS) { // per-warp item parity and "previous item pending" flag
+        reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[48] = 0;
+        reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[49] = 0;
+    }
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = uni(threadIdx.x >> 5);
     // per-warp row ring: UN_SLOTS slots of one row (+16 bytes) each
@@ -531,12 +557,12 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     sc.bytes = p.bytes;
     sc.abs_base = p.abs_base;
     sc.offsets = p.offsets;
-    sc.items = p.items;
     sc.vtab_g = p.vtab;
     sc.vtab_sa = saddr_of(s_vtab);
     sc.vtab_in_smem = p.vtab_in_smem;
-    sc.scratch_sa = saddr_of(scratch_all) + warp * 128;
-    sc.s_counts = p.counts_in_smem ? s_counts : nullptr;
+    sc.one_off = p.vtab_one_off;
+    sc.scratch_sa = saddr_of(scratch_all) + warp * 256;
+    sc.s_counts_sa = p.counts_in_smem ? saddr_of(s_counts) : 0u;
     sc.g_counts = p.uniq_counts;
 
     uint32_t qn = 0;         // pending events
@@ -555,12 +581,29 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             if (lane == 0) atomicOr(&p.work[1], 1u);
             continue;
         }
+        // What the slow path needs to know about this item goes into the scratch set of the item's parity.  The set
+        // still belongs to the item before the previous one; its events are gone unless the list has not been
+        // emptied since then (flag word 49: "the list holds events of the previous item"), in which case it is now.
+        const uint2 st = lds64v(sc.scratch_sa + 192); // parity of the previous item, pending flag
+        const uint32_t par = st.x ^ 1u;
+        if (qn && st.y) {
+            carry = drain_events(sc, q_sa, qn, carry, lutlane, mul);
+            qn = 0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t set_sa = sc.scratch_sa + (par << 5);
+            sts128v(set_sa, ks, ke, (uint32_t)b_abs, (uint32_t)(b_abs >> 32));
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(set_sa + 16), "r"((uint32_t)e_abs), "r"((uint32_t)(e_abs >> 32)) : "memory");
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sc.scratch_sa + 192), "r"(par), "r"(qn ? 1u : 0u) : "memory");
+        }
         const uint64_t row0 = b_abs & ~127ull; // absolute position of the item's first row
         const uint8_t *text = p.bytes + (row0 - p.abs_base);
         const uint32_t e_rel = (uint32_t)(e_abs - row0);
         const uint32_t load_end = (e_rel + 15u) & ~15u;
         const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
-        const uint32_t g32 = (uint32_t)((row0 - p.abs_base) >> 5) + lane; // my group's index in row 0, in 32-byte units
+        // my group's index in row 0, in 32-byte units (< 2^31: a batch is below 64 GiB), and the item's parity
+        const uint32_t g32 = ((uint32_t)((row0 - p.abs_base) >> 5) + lane) | par << 31;
 
         // Every lane copies its own 32 bytes (lane 31 also the 16 bytes after the row -- they follow its own
         // -- into the slot's tail) with 16-byte asynchronous copies.  One commit group per call, also when there is nothing left to copy, so
@@ -590,7 +633,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             __syncwarp(); // my lookahead is the next lane's copy
             const uint32_t base = ring_sa + slot * UN_SLOT_BYTES;
             const uint4 c0 = lds128v(base + off0), c1 = lds128v(base + off1);
-            const uint32_t la = lds32v(base + offla);
+            const uint2 la2 = lds64v(base + offla); // the 8 bytes after my group
+            const uint32_t la = la2.x;
 
             // ---- shift-and filter over 35 bytes ---------------------------------------------------
             // Reports are collected per quarter of the group: acc[k] covers the steps at which starts
@@ -642,12 +686,13 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                 if (qn + n > UN_QCAP) {
                     carry = drain_events(sc, q_sa, qn, carry, lutlane, mul);
                     qn = 0;
+                    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sc.scratch_sa + 196), "r"(0u) : "memory"); // nothing older pending
                 }
                 if (flag) {
                     const uint32_t e = q_sa + (qn + __popc(m & lt)) * (UN_Q_WORDS * 4);
                     sts128v(e, c0.x, c0.y, c0.z, c0.w);
                     sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
-                    sts128v(e + 32, la, g32 + (r << 5), tops, item);
+                    sts128v(e + 32, la, la2.y, g32 + (r << 5), tops);
                 }
                 qn += n;
             }
@@ -761,6 +806,7 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     p.vtab_in_smem = vtab_in_smem ? 1u : 0u;
     p.vtab = ctx->dev.vtab;
     p.vtab_words = h.vtab_words;
+    p.vtab_one_off = h.vtab[5];
     p.mul256 = 256u;
     p.uniq_counts = (unsigned long long *)d_uniq_counts;
     p.pat_to_uniq = ctx->dev.pat_to_uniq;

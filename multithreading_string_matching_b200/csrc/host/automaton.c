@@ -359,92 +359,77 @@ static int build_dfa(kmpb_tables *t)
 
 /* ---- start-anchored verification tables ---------------------------------------------------------- */
 
-#define VT_LENS_SLOTS 1024 /* key-length masks, one byte per hash slot of a pattern's first two bytes */
-#define VT_HEADER (12 + VT_LENS_SLOTS / 4)
-#define VT_EMPTY 0xffffffffu
+#define VT_HEADER 8
 
-uint32_t kmpb_vtab_hash(uint32_t key, uint32_t mask) { return ((key * 0x9e3779b1u) >> 12) & mask; }
+/* slot of a text position's first two bytes (little-endian u16) in a table of 1 << (32 - shift) slots */
+uint32_t kmpb_vtab_slot(uint32_t first2, uint32_t shift) { return ((first2 & 0xffffu) * 0x9e3779b1u) >> shift; }
 
-/* slot of a text position's first two bytes (little-endian u16) in the key-length masks */
-uint32_t kmpb_vtab_lens_slot(uint32_t first2) { return ((first2 & 0xffffu) * 0x9e3779b1u) >> 22; }
-
-/* first min(len,4) bytes of a pattern as a little-endian word */
-static uint32_t key_of(const uint8_t *p, uint32_t len)
+static uint32_t word_of(const uint8_t *p, uint32_t len, uint32_t from)
 {
     uint32_t k = 0;
-    for (uint32_t i = 0; i < 4 && i < len; i++) k |= (uint32_t)p[i] << (8 * i);
+    for (uint32_t i = from; i < from + 4 && i < len; i++) k |= (uint32_t)p[i] << (8 * (i - from));
+    return k;
+}
+static uint32_t mask_of(uint32_t len, uint32_t from)
+{
+    uint32_t k = 0;
+    for (uint32_t i = from; i < from + 4 && i < len; i++) k |= 0xffu << (8 * (i - from));
     return k;
 }
 
 static int build_verify_tables(kmpb_tables *t)
 {
-    uint32_t count[5] = {0, 0, 0, 0, 0}, slots[5] = {0, 0, 0, 0, 0}, toff[5] = {0, 0, 0, 0, 0};
-    uint32_t blob_words = 0;
+    /* one slot per hash value of a pattern's first two bytes; at least four slots per pattern of two or more bytes,
+     * so most slots are empty and most occupied slots hold the patterns of a single two-byte prefix */
+    uint32_t n2 = 0, n1 = 0, blob_words = 0;
     for (uint32_t u = 0; u < t->n_uniq; u++) {
-        uint32_t L = t->uniq_len[u] < 4 ? t->uniq_len[u] : 4;
-        count[L]++;
+        if (t->uniq_len[u] >= 2) n2++; else n1++;
         blob_words += (t->uniq_len[u] + 3) / 4;
     }
+    uint32_t log_slots = 6;
+    while (log_slots < 16 && (1u << log_slots) < 4 * n2) log_slots++;
+    const uint32_t slots = 1u << log_slots, shift = 32 - log_slots;
     uint32_t at = VT_HEADER;
-    for (uint32_t L = 1; L <= 4; L++) {
-        if (count[L] == 0) continue;
-        uint32_t n = 8;
-        while (n < 4 * count[L]) n *= 2; /* load factor <= 0.25: short probe sequences */
-        if (n > (1u << 20)) return kmpb_fail(KMPB_ELIMIT, "too many patterns for the verification tables");
-        slots[L] = n;
-        toff[L] = at;
-        at += 2 * n;
-    }
+    const uint32_t slot_off = at;
+    at += 2 * slots;
+    const uint32_t one_off = n1 ? at : 0;
+    if (n1) at += 256;
     at = (at + 3u) & ~3u; /* records are read 16 bytes at a time */
     const uint32_t rec_off = at;
-    at += 4 * t->n_uniq;
+    at += 8 * n2;
     const uint32_t blob_off = at;
     at += blob_words;
     uint32_t *v = calloc(at ? at : 1, sizeof *v);
-    if (!v) return kmpb_fail(KMPB_ENOMEM, "out of memory building the verification tables");
-    v[0] = at;
-    for (uint32_t L = 1; L <= 4; L++) {
-        v[L] = toff[L];
-        v[4 + L] = slots[L] ? slots[L] - 1 : 0;
-        if (slots[L]) v[11] |= 1u << (L - 1);
-        for (uint32_t s = 0; s < slots[L]; s++) v[toff[L] + 2 * s + 1] = VT_EMPTY;
+    uint32_t *fill = calloc(slots, sizeof *fill);
+    if (!v || !fill) { free(v); free(fill); return kmpb_fail(KMPB_ENOMEM, "out of memory building the verification tables"); }
+    v[0] = at; v[1] = slot_off; v[2] = shift; v[3] = rec_off; v[4] = blob_off; v[5] = one_off;
+    for (uint32_t i = 0; n1 && i < 256; i++) v[one_off + i] = 0xffffffffu;
+    /* chain lengths, then chain starts (records of one slot are contiguous) */
+    for (uint32_t u = 0; u < t->n_uniq; u++) {
+        const uint8_t *p = t->uniq_blob + t->uniq_off[u];
+        if (t->uniq_len[u] >= 2) v[slot_off + 2 * kmpb_vtab_slot(p[0] | (uint32_t)p[1] << 8, shift) + 1]++;
     }
-    v[9] = rec_off;
-    v[10] = blob_off;
+    for (uint32_t s = 0, first = 0; s < slots; s++) {
+        v[slot_off + 2 * s] = first;
+        first += v[slot_off + 2 * s + 1];
+    }
     uint32_t bw = 0;
     for (uint32_t u = 0; u < t->n_uniq; u++) {
         const uint8_t *p = t->uniq_blob + t->uniq_off[u];
-        const uint32_t len = t->uniq_len[u], L = len < 4 ? len : 4, key = key_of(p, len);
-        uint32_t *rec = v + rec_off + 4 * u;
-        rec[0] = len | bw << 8;
-        rec[1] = rec[2] = 0; /* pattern bytes 4..7 and the mask of those that exist */
-        for (uint32_t i = 4; i < 8 && i < len; i++) {
-            rec[1] |= (uint32_t)p[i] << (8 * (i - 4));
-            rec[2] |= 0xffu << (8 * (i - 4));
-        }
-        rec[3] = VT_EMPTY;
+        const uint32_t len = t->uniq_len[u];
         memcpy((uint8_t *)(v + blob_off + bw), p, len); /* rest of the last word stays zero */
-        bw += (len + 3) / 4;
-        /* which key lengths can start with these two bytes (a 1-byte pattern: any second byte) */
-        if (len >= 2) ((uint8_t *)(v + 12))[kmpb_vtab_lens_slot(p[0] | (uint32_t)p[1] << 8)] |= (uint8_t)(1u << (L - 1));
-        else for (uint32_t b1 = 0; b1 < 256; b1++) ((uint8_t *)(v + 12))[kmpb_vtab_lens_slot(p[0] | b1 << 8)] |= 1u;
-        /* insert: same key -> chain (only possible for len >= 4; shorter patterns are distinct keys) */
-        uint32_t s = kmpb_vtab_hash(key, slots[L] - 1);
-        for (;;) {
-            uint32_t *slot = v + toff[L] + 2 * s;
-            if (slot[1] == VT_EMPTY) {
-                slot[0] = key;
-                slot[1] = u;
-                break;
-            }
-            if (slot[0] == key) {
-                rec[3] = slot[1]; /* push front */
-                slot[1] = u;
-                break;
-            }
-            s = (s + 1) & (slots[L] - 1);
+        if (len >= 2) {
+            const uint32_t s = kmpb_vtab_slot(p[0] | (uint32_t)p[1] << 8, shift);
+            uint32_t *rec = v + rec_off + 8 * (v[slot_off + 2 * s] + fill[s]++);
+            rec[0] = word_of(p, len, 0); rec[1] = mask_of(len, 0);
+            rec[2] = word_of(p, len, 4); rec[3] = mask_of(len, 4);
+            rec[4] = len; rec[5] = u; rec[6] = bw; rec[7] = 0;
+        } else {
+            v[one_off + p[0]] = u;
         }
+        bw += (len + 3) / 4;
     }
+    free(fill);
     t->vtab = v;
     t->vtab_words = at;
     return KMPB_OK;

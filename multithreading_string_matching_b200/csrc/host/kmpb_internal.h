@@ -50,17 +50,15 @@ typedef struct kmpb_tables {
     uint32_t filter[256];
     uint32_t bucket_of_uniq_valid; /* 1 when filter[] is usable (n_uniq > 0) */
 
-    /* start-anchored verification tables (the device's slow path): one open-addressing hash table per
-     * key length L = 1..4, keyed by the first min(len, 4) bytes of a pattern (little-endian u32).
+    /* start-anchored verification tables (the device's slow path): the patterns of two or more bytes, grouped by
+     * the hash of their first two bytes; a text position probes one slot and compares the records of that slot.
      * Layout of vtab (u32 words):
-     *   [0] total words   [1..4] word offset of table L (0 = none)   [5..8] slot mask of table L
-     *   [9] word offset of the records   [10] word offset of the pattern words   [11] bit L-1 set when table L exists
-     *   [12..267] 1024 bytes: byte kmpb_vtab_lens_slot(first two text bytes) has bit L-1 set when some pattern with
-     *            key length L starts with those two bytes (a 1-byte pattern: with that byte)
-     *   tables: slots of 2 words {key, first record or 0xffffffff}
-     *   records (4 words per distinct pattern, 16-byte aligned): {length | word offset of its bytes inside the
-     *            pattern words << 8, pattern bytes 4..7 (zero padded), mask of those bytes that exist,
-     *            next record with the same 4-byte key or 0xffffffff}
+     *   [0] total words   [1] word offset of the slots   [2] hash shift (slots = 1 << (32 - shift))
+     *   [3] word offset of the records   [4] word offset of the pattern words
+     *   [5] word offset of the one-byte patterns' table (256 words: distinct id or 0xffffffff), 0 = there are none
+     *   slots: 2 words {first record, number of records} -- the patterns whose first two bytes hash to this slot
+     *   records (8 words, 16-byte aligned): {pattern bytes 0..3, mask of those that exist, bytes 4..7, their mask,
+     *            length, distinct id, word offset of the pattern's bytes inside the pattern words, 0}
      *   pattern words: every pattern zero-padded to a multiple of 4 bytes */
     uint32_t *vtab;
     uint32_t vtab_words;
@@ -74,9 +72,8 @@ uint64_t kmpb_pcap_chunk_end(const kmpb_pcap *pc, uint64_t first, uint64_t last,
                              uint64_t *bytes_out);
 void kmpb_pcap_pack(const kmpb_pcap *pc, uint64_t first, uint64_t count, uint8_t *dst, uint64_t *offsets);
 
-/* slot of `key` in a verification table with `mask`+1 slots (the device uses the same expression) */
-uint32_t kmpb_vtab_hash(uint32_t key, uint32_t mask);
-uint32_t kmpb_vtab_lens_slot(uint32_t first2);
+/* slot of a text position's first two bytes in the verification tables (the device uses the same expression) */
+uint32_t kmpb_vtab_slot(uint32_t first2, uint32_t shift);
 int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat);
 void kmpb_tables_free(kmpb_tables *t);
 

@@ -75,32 +75,32 @@ static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int
     for (uint32_t u = 0; u < t.n_uniq; u++)
         if (got_trie[u] != got[u]) { fprintf(stderr, "uniq %u: trie %llu dfa %llu\n", u, (unsigned long long)got_trie[u], (unsigned long long)got[u]); bad = 1; }
     free(got_trie);
-    /* 1c. the hash verification tables, probed at every start position, report the same counts */
+    /* 1c. the verification tables, probed at every start position the way the device probes them (one slot per
+     *     position, masked compare of the first 8 bytes, then the remaining pattern words), report the same counts */
     if (t.n_uniq) {
         const uint32_t *v = t.vtab;
         uint64_t *got_hash = calloc((size_t)t.n_uniq + 1, sizeof *got_hash);
+        uint32_t n_rec = 0;
+        for (uint32_t s = 0; s < (1u << (32 - v[2])); s++) {
+            if (v[v[1] + 2 * s] != n_rec) { fprintf(stderr, "slot %u: chains are not contiguous\n", s); bad = 1; }
+            n_rec += v[v[1] + 2 * s + 1];
+        }
         for (int s = 0; s < text_len; s++) {
-            uint32_t x0 = 0;
+            uint32_t x0 = 0, x1 = 0;
             for (int k = 0; k < 4; k++) x0 |= (uint32_t)text[s + k] << (8 * k); /* text is zero padded */
-            for (uint32_t L = 1; L <= 4; L++) {
-                if (!((v[11] >> (L - 1)) & 1u)) continue;
-                if (!((((const uint8_t *)(v + 12))[kmpb_vtab_lens_slot(x0)] >> (L - 1)) & 1u)) continue; /* key-length mask, as the device probes */
-                const uint32_t key = L == 4 ? x0 : x0 & ((1u << (8 * L)) - 1u), mask = v[4 + L];
-                for (uint32_t slot = kmpb_vtab_hash(key, mask);; slot = (slot + 1) & mask) {
-                    const uint32_t *e = v + v[L] + 2 * slot;
-                    if (e[1] == 0xffffffffu) break;
-                    if (e[0] != key) continue;
-                    for (uint32_t u = e[1]; u != 0xffffffffu; u = v[v[9] + 4 * u + 3]) {
-                        const uint32_t len = v[v[9] + 4 * u] & 0xffu;
-                        const uint8_t *pb = (const uint8_t *)(v + v[10] + (v[v[9] + 4 * u] >> 8));
-                        uint32_t x1 = 0; /* the inlined second word agrees with the pattern bytes */
-                        for (uint32_t k = 4; k < 8 && k < len; k++) x1 |= (uint32_t)pb[k] << (8 * (k - 4));
-                        if (x1 != v[v[9] + 4 * u + 1] || (len > 4 && v[v[9] + 4 * u + 2] != (len >= 8 ? 0xffffffffu : (1u << (8 * (len - 4))) - 1u))
-                            || (len <= 4 && v[v[9] + 4 * u + 2] != 0)) { fprintf(stderr, "record %u: inlined word wrong\n", u); bad = 1; }
-                        if (s + (int)len <= text_len && memcmp(text + s, pb, len) == 0) got_hash[u]++;
-                    }
-                    break;
-                }
+            for (int k = 0; k < 4; k++) x1 |= (uint32_t)text[s + 4 + k] << (8 * k);
+            if (v[5] && v[v[5] + (x0 & 0xffu)] != 0xffffffffu) got_hash[v[v[5] + (x0 & 0xffu)]]++;
+            const uint32_t *e = v + v[1] + 2 * kmpb_vtab_slot(x0, v[2]);
+            for (uint32_t r = 0; r < e[1]; r++) {
+                const uint32_t *rec = v + v[3] + 8 * (e[0] + r);
+                const uint32_t len = rec[4], u = rec[5];
+                const uint8_t *pb = (const uint8_t *)(v + v[4] + rec[6]);
+                if (u >= t.n_uniq || len != t.uniq_len[u] || len < 2 || memcmp(pb, t.uniq_blob + t.uniq_off[u], len)) { fprintf(stderr, "record of slot: wrong pattern\n"); bad = 1; break; }
+                if (((x0 ^ rec[0]) & rec[1]) | ((x1 ^ rec[2]) & rec[3])) continue;
+                if (s + (int)len > text_len) continue;
+                if (len > 8 && memcmp(text + s + 8, pb + 8, len - 8)) continue;
+                if (memcmp(text + s, pb, len)) { fprintf(stderr, "record masks wrong for uniq %u\n", u); bad = 1; }
+                got_hash[u]++;
             }
         }
         for (uint32_t u = 0; u < t.n_uniq; u++)
