@@ -59,14 +59,25 @@ constexpr int UN_WARPS = UN_THREADS / 32;
 constexpr uint32_t UN_GRP = 32;                           // bytes per lane per row
 constexpr uint32_t UN_ROW = 32 * UN_GRP;                  // bytes per warp row
 constexpr uint32_t UN_SLOTS = KMPB_UN_SLOTS;              // rows in flight per warp (cp.async -> shared memory)
-constexpr uint32_t UN_SLOT_BYTES = UN_ROW + 16;           // a row and the 16 bytes after it (lookahead)
+// KMPB_UN_SLOTS == 2: a slot holds a row and the 16 bytes after it (lane 31's lookahead, copied by lane 31).
+// KMPB_UN_SLOTS == 3: a slot holds a row; two rows are complete when a row is scanned, and lane 31 finds its
+// lookahead at the start of the next slot (no tail copy).
+constexpr bool UN_TAIL = KMPB_UN_SLOTS < 3;
+constexpr uint32_t UN_SLOT_BYTES = UN_ROW + (UN_TAIL ? 16 : 0);
 constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item size
 #ifndef KMPB_UN_TAIL_ITEMS
 #define KMPB_UN_TAIL_ITEMS 16384
 #endif
 constexpr uint32_t UN_TAIL_ITEMS = KMPB_UN_TAIL_ITEMS;   // quarter-size items at the end of a batch (about one per warp x 4)
-constexpr uint32_t UN_QCAP = 32;                          // events per warp list
+#ifndef KMPB_UN_QCAP
+#define KMPB_UN_QCAP 32
+#endif
+constexpr uint32_t UN_QCAP = KMPB_UN_QCAP;                          // events per warp list
 constexpr uint32_t UN_Q_WORDS = 12; // event: 32 B group, 8 B lookahead, group index | item parity << 31, quarter reports (48 B)
+#ifndef KMPB_UN_DENSE
+#define KMPB_UN_DENSE 8
+#endif
+constexpr uint32_t UN_DENSE = KMPB_UN_DENSE; // reporting groups per row from which superseded NUL-only events are dropped (> 32: never)
 constexpr uint32_t UN_LUT_BYTES = 256 * 256; // 256-byte row per byte value; lanes use the first 128 B
 constexpr uint32_t FULL = 0xffffffffu;
 
@@ -261,7 +272,7 @@ struct slow_ctx {
     uint32_t vtab_in_smem;
     uint32_t one_off;       // word offset of the one-byte patterns' table, 0 = none
     uint32_t scratch_sa;    // per-warp scratch: {ks, ke, b_abs, e_abs} of the items of either parity (2 x 32 B),
-                            // 32 words the resolve step publishes, item parity and the "previous item pending" flag
+                            // 32 words the resolve step publishes, item parity, the "previous item pending" flag, the NUL carry
     uint32_t s_counts_sa;   // shared address of the shared counters, or 0
     unsigned long long *g_counts;
 };
@@ -335,8 +346,9 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, const verify_ctx
     }
 }
 
-// Resolve the warp's n pending events (n <= 32).  carry = 1 + absolute position of the last NUL byte
-// seen in the events resolved so far by this warp (0 = none); returns the new carry.
+// Resolve the warp's n pending events (n <= 32).  The warp's carry -- 1 + absolute position of the last NUL byte
+// seen in the events it has resolved so far (0 = none) -- lives in its scratch words (bytes 200..207), not in a
+// register of the row loop.
 //
 // Phase 1, one event per lane: which start positions fired, where the NULs are, which packet(s) the
 // group lies in -> mask of candidate starts that are alive (inside the item, no NUL before them in their
@@ -348,8 +360,8 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, const verify_ctx
 // that); an event carries its item's parity, and the packets [ks, ke) and bytes [b_abs, e_abs) of both items wait in
 // the warp's scratch words, where the warp put them when it took the item: no lane has to look them up in global
 // memory, and the row loop does not keep them in registers.
-__device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t q_sa, const uint32_t n, uint64_t carry,
-                                              const uint32_t lutlane, const uint32_t mul)
+__device__ __noinline__ void drain_events(const slow_ctx &c, const uint32_t q_sa, const uint32_t n, const uint32_t lutlane,
+                                          const uint32_t mul)
 {
     const uint32_t lane = threadIdx.x & 31;
     __syncwarp();
@@ -397,9 +409,13 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
     const uint32_t nulm = __ballot_sync(FULL, zm != 0);
     const uint32_t below = nulm & ((1u << lane) - 1u);
     const uint64_t from_below = __shfl_sync(FULL, mylast1, below ? 31 - __clz(below) : 0);
+    const uint2 cw = lds64v(c.scratch_sa + 200);
+    const uint64_t carry = (uint64_t)cw.y << 32 | cw.x;
     const uint64_t prev1 = below ? from_below : carry;
     const uint64_t from_top = __shfl_sync(FULL, mylast1, nulm ? 31 - __clz(nulm) : 0);
-    if (nulm) carry = from_top;
+    __syncwarp();
+    if (nulm && lane == 0)
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(c.scratch_sa + 200), "r"((uint32_t)from_top), "r"((uint32_t)(from_top >> 32)) : "memory");
 
     uint32_t am = 0, bm = 0, nextb = 255; // alive candidates; packet starts inside the group (bit = offset);
                                           // offset of the first packet start at or after the group's end
@@ -491,7 +507,19 @@ __device__ __noinline__ uint64_t drain_events(const slow_ctx &c, const uint32_t 
         }
     }
     __syncwarp();
-    return carry;
+}
+
+// NUL-dense row (many groups reported and the list is full).  An event without candidates exists only to tell later
+// candidates where the last NUL before them is; when the next event of the row is of the same kind, that one tells
+// them a later NUL and this one is not needed: its reports are cleared (binary payloads: one event per row instead
+// of one per group).  m = lanes with reports.  Kept out of line: the row loop should stay small.
+__device__ __noinline__ uint32_t drop_superseded(uint32_t tops, const uint32_t m)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t mc = __ballot_sync(FULL, (tops & 0x7f7f7f7fu) != 0); // lanes with candidates
+    const uint32_t above = m & ~((2u << lane) - 1u);                    // reporting lanes above me
+    if (!((mc >> lane) & 1u) && above && !((mc >> (__ffs(above) - 1)) & 1u)) tops = 0;
+    return tops;
 }
 
 // warp-uniform value, in a form the compiler can keep in a uniform register
@@ -531,6 +559,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     if (threadIdx.x < UN_WARPS) { // per-warp item parity and "previous item pending" flag
         reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[48] = 0;
         reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[49] = 0;
+        reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[50] = 0; // the warp's NUL carry
+        reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[51] = 0;
     }
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = uni(threadIdx.x >> 5);
@@ -543,6 +573,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     const uint32_t off0 = lane * UN_GRP, off1 = off0 + 16, offla = off0 + UN_GRP;
 #else
     const uint32_t off0 = lane * UN_GRP + ((lane >> 2) & 1u) * 16, off1 = off0 ^ 16u;
+    // lane 31's lookahead: the slot's tail, or (three slots) the first bytes of the following slot
     const uint32_t offla = lane == 31 ? UN_ROW : (lane + 1) * UN_GRP + (((lane + 1) >> 2) & 1u) * 16;
 #endif
     __syncthreads();
@@ -566,7 +597,6 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     sc.g_counts = p.uniq_counts;
 
     uint32_t qn = 0;         // pending events
-    uint64_t carry = 0;      // 1 + position of the last NUL among the events resolved so far
 
     for (;;) {
         uint32_t item = 0;
@@ -587,7 +617,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         const uint2 st = lds64v(sc.scratch_sa + 192); // parity of the previous item, pending flag
         const uint32_t par = st.x ^ 1u;
         if (qn && st.y) {
-            carry = drain_events(sc, q_sa, qn, carry, lutlane, mul);
+            drain_events(sc, q_sa, qn, lutlane, mul);
             qn = 0;
         }
         __syncwarp();
@@ -598,7 +628,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sc.scratch_sa + 192), "r"(par), "r"(qn ? 1u : 0u) : "memory");
         }
         const uint64_t row0 = b_abs & ~127ull; // absolute position of the item's first row
-        const uint8_t *text = p.bytes + (row0 - p.abs_base);
+        const uint8_t *textl = p.bytes + (row0 - p.abs_base) + lane * UN_GRP; // my 32 bytes of the item's first row
         const uint32_t e_rel = (uint32_t)(e_abs - row0);
         const uint32_t load_end = (e_rel + 15u) & ~15u;
         const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
@@ -611,17 +641,18 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         // scanned has arrived".  (A chunk-major slot layout, free of bank conflicts on both sides, measured
         // 14 % slower on the fast path alone.)
         auto issue_row = [&](uint32_t r, uint32_t slot) {
-            const uint32_t row = r * UN_ROW, g = row + lane * UN_GRP;
+            const uint32_t row = r * UN_ROW;
             const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES;
-            const uint8_t *src = add_wide(text, g); // one multiply-add on the FMA pipe instead of two ALU adds
+            const uint8_t *src = add_wide(textl, row); // one multiply-add on the FMA pipe instead of two ALU adds
             if (row + UN_SLOT_BYTES <= load_end) {
                 cp_async16(dst + off0, src);
                 cp_async16(dst + off1, src + 16);
-                cp_async16_if(lane == 31, dst + offtail, src + 32);
-            } else if (r < nrows) {
+                if (UN_TAIL) cp_async16_if(lane == 31, dst + offtail, src + 32);
+            } else if (row < e_rel) { // r < nrows
+                const uint32_t g = row + lane * UN_GRP;
                 if (g < load_end) cp_async16(dst + off0, src);
                 if (g + 16 < load_end) cp_async16(dst + off1, src + 16);
-                if (lane == 31 && g + 32 < load_end) cp_async16(dst + offtail, src + 32);
+                if (UN_TAIL && lane == 31 && g + 32 < load_end) cp_async16(dst + offtail, src + 32);
             }
             cp_async_commit();
         };
@@ -629,11 +660,12 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
 
         // one row: wait for its slot, filter, refill the slot, push the events
         auto scan_row = [&](const uint32_t r, const uint32_t slot) {
-            cp_async_wait<UN_SLOTS - 1>();
+            cp_async_wait<UN_TAIL ? UN_SLOTS - 1 : UN_SLOTS - 2>();
             __syncwarp(); // my lookahead is the next lane's copy
             const uint32_t base = ring_sa + slot * UN_SLOT_BYTES;
             const uint4 c0 = lds128v(base + off0), c1 = lds128v(base + off1);
-            const uint2 la2 = lds64v(base + offla); // the 8 bytes after my group
+            // the 8 bytes after my group: the next lane's, for lane 31 the first of the next row (next slot)
+            const uint2 la2 = lds64v(UN_TAIL || slot + 1 < UN_SLOTS || lane != 31 ? base + offla : ring_sa);
             const uint32_t la = la2.x;
 
             // ---- shift-and filter over 35 bytes ---------------------------------------------------
@@ -672,8 +704,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             acc3 |= accC & 0x7f000000u;
             // the four top bytes side by side: quarter k has something to resolve iff byte k is nonzero
             const uint32_t tops = __byte_perm(__byte_perm(acc0, acc1, 0x0073), __byte_perm(acc2, acc3, 0x0073), 0x5410);
-            const bool flag = tops != 0;
-            const uint32_t m = __ballot_sync(FULL, flag);
+            const uint32_t m = __ballot_sync(FULL, tops != 0);
 
             // every lane holds its bytes: refill the slot with the row UN_SLOTS ahead
             issue_row(r + UN_SLOTS, slot);
@@ -683,12 +714,29 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
 #endif
             if (m) {
                 const uint32_t n = __popc(m);
-                if (qn + n > UN_QCAP) {
-                    carry = drain_events(sc, q_sa, qn, carry, lutlane, mul);
+                auto resolve_pending = [&]() {
+                    drain_events(sc, q_sa, qn, lutlane, mul);
                     qn = 0;
                     if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sc.scratch_sa + 196), "r"(0u) : "memory"); // nothing older pending
+                };
+                if (qn + n > UN_QCAP) { // the list cannot take this row's events
+                    if (UN_DENSE <= 32 && n >= UN_DENSE) {
+                        // NUL-dense row: its own (rare) path, so that the usual one keeps its registers
+                        const uint32_t tops2 = drop_superseded(tops, m);
+                        const uint32_t m2 = __ballot_sync(FULL, tops2 != 0), n2 = __popc(m2);
+                        if (qn + n2 > UN_QCAP) resolve_pending();
+                        if (tops2 != 0) {
+                            const uint32_t e = q_sa + (qn + __popc(m2 & lt)) * (UN_Q_WORDS * 4);
+                            sts128v(e, c0.x, c0.y, c0.z, c0.w);
+                            sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
+                            sts128v(e + 32, la, la2.y, g32 + (r << 5), tops2);
+                        }
+                        qn += n2;
+                        return;
+                    }
+                    resolve_pending();
                 }
-                if (flag) {
+                if (tops != 0) {
                     const uint32_t e = q_sa + (qn + __popc(m & lt)) * (UN_Q_WORDS * 4);
                     sts128v(e, c0.x, c0.y, c0.z, c0.w);
                     sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
@@ -704,6 +752,13 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             scan_row(r, 0);
             if (r + 1 < nrows) scan_row(r + 1, 1);
         }
+#elif KMPB_UN_SLOTS == 3
+#pragma unroll 1
+        for (uint32_t r = 0; r < nrows; r += 3) {
+            scan_row(r, 0);
+            if (r + 1 < nrows) scan_row(r + 1, 1);
+            if (r + 2 < nrows) scan_row(r + 2, 2);
+        }
 #else
         uint32_t slot = 0;
 #pragma unroll 1
@@ -714,7 +769,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
 #endif
     }
     // leftovers
-    if (qn) carry = drain_events(sc, q_sa, qn, carry, lutlane, mul);
+    if (qn) drain_events(sc, q_sa, qn, lutlane, mul);
 
     __syncthreads();
     if (p.counts_in_smem)
@@ -768,13 +823,16 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     if (b.end_byte - b.abs_base >= (1ull << 36))
         return kmpb_fail(KMPB_ELIMIT, "more than 64 GiB of payload in one batch");
     const uint64_t span = b.end_byte - b.first_byte;
+    // Taking an item costs a warp three dependent trips to L2 (ticket, item table, offsets); large batches
+    // afford larger items (C3, 14 GB: 64 KB items 2.96 TB/s, 256 KB items 3.00 TB/s).
+    const uint64_t item_bytes = span >= (8ull << 30) ? 4ull * UN_ITEM_BYTES : span >= (4ull << 30) ? 2ull * UN_ITEM_BYTES : UN_ITEM_BYTES;
     // full-size items, except the last UN_TAIL_ITEMS/4 items' worth of bytes (at most an eighth of the batch),
     // which is cut into quarter-size items
-    const uint64_t whole = span / UN_ITEM_BYTES;
+    const uint64_t whole = span / item_bytes;
     const uint64_t tail_items = std::min<uint64_t>(UN_TAIL_ITEMS / 4, whole / 8); // at most an eighth of the batch
     const uint32_t n_big = (uint32_t)(whole - tail_items);
-    const uint64_t small_span = span - (uint64_t)n_big * UN_ITEM_BYTES;
-    const uint32_t n_items = n_big + (uint32_t)((small_span + UN_ITEM_BYTES / 4 - 1) / (UN_ITEM_BYTES / 4));
+    const uint64_t small_span = span - (uint64_t)n_big * item_bytes;
+    const uint32_t n_items = n_big + (uint32_t)((small_span + item_bytes / 4 - 1) / (item_bytes / 4));
     if ((size_t)n_items + 1 > ctx->items_cap) return kmpb_fail(KMPB_ESTATE, "union scratch too small");
     uint32_t *d_items = ctx->d_items + (size_t)slot * ctx->items_cap;
     uint32_t *d_work = ctx->d_work + slot * 4;
@@ -791,7 +849,7 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
         ctx->attr_union_set = true;
     }
     kmpb_union_partition_kernel<<<(n_items + 1 + 255) / 256, 256, 0, stream>>>(b.d_offsets, (uint32_t)b.n_packets, n_items,
-                                                                              n_big, UN_ITEM_BYTES, d_items, d_work);
+                                                                              n_big, item_bytes, d_items, d_work);
     union_params p;
     p.bytes = b.d_bytes;
     p.abs_base = b.abs_base;

@@ -21,7 +21,7 @@ m = kmp.Matcher(0, engine="union")
 t0, rounds, total_bytes = time.time(), 0, 0
 while time.time() - t0 < budget:
     alpha = bytes(rng.sample(range(1, 256), rng.choice((2, 3, 5, 26, 95))))
-    p_nul = rng.choice((0.0, 0.0005, 0.01, 0.2))
+    p_nul = rng.choice((0.0, 0.0005, 0.01, 0.2, 0.7, 0.97))
     n_pat = rng.choice((1, 3, 17, 97, 300))
     max_len = rng.choice((2, 4, 7, 13, 40, 99))
     pats = [bytes(rng.choice(alpha) for _ in range(rng.randint(1, max_len))) for _ in range(n_pat)]
