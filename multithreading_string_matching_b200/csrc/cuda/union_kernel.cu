@@ -62,7 +62,10 @@ constexpr uint32_t UN_SLOTS = KMPB_UN_SLOTS;              // rows in flight per 
 // KMPB_UN_SLOTS == 2: a slot holds a row and the 16 bytes after it (lane 31's lookahead, copied by lane 31).
 // KMPB_UN_SLOTS == 3: a slot holds a row; two rows are complete when a row is scanned, and lane 31 finds its
 // lookahead at the start of the next slot (no tail copy).
-constexpr bool UN_TAIL = KMPB_UN_SLOTS < 3;
+#ifndef KMPB_UN_TAIL
+#define KMPB_UN_TAIL (KMPB_UN_SLOTS < 3)
+#endif
+constexpr bool UN_TAIL = KMPB_UN_TAIL;
 constexpr uint32_t UN_SLOT_BYTES = UN_ROW + (UN_TAIL ? 16 : 0);
 constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item size
 #ifndef KMPB_UN_TAIL_ITEMS
