@@ -551,6 +551,13 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    # stdout carries the one JSON line and nothing else: whatever libraries write to file descriptor 1 in the
+    # meantime (NCCL prints its version there when the box sets NCCL_DEBUG) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = json_out
+
     import multithreading_string_matching_b200 as kmp  # raises if libkmpb200.so is missing: no fallback
 
     patterns = kmp.load_patterns(os.path.join(DATA, "strings.txt"))
