@@ -15,25 +15,26 @@
 //  integer multiply-add (FMA pipe), the AND one LOP3 (ALU pipe).  Bits 24..30 of S say "the last 4
 //  bytes are the first 4 bytes (or all the bytes) of some pattern of bucket b"; bit 31 says "this
 //  byte is NUL".  The reports are OR-ed per quarter of the group (8 start positions); a lane with any
-//  report appends an EVENT -- its 36 bytes, where they are, and which quarters reported -- to the warp's
-//  list in shared memory.  That is all: one ballot and (usually) a few stores per row on top of the
-//  filter.
+//  report appends an EVENT -- its 32 bytes and the 8 after them, where they are, and which quarters reported -- to
+//  the warp's list in shared memory.  That is all: one ballot and (usually) a few stores per row on top of the
+//  filter.  (When the list is full and a row reports from many groups -- NUL-dense payloads -- events that hold
+//  only NULs and are superseded by a later one of the same row are dropped first: drop_superseded.)
 //
 //  SLOW PATH (events only).  When the list cannot take the next row's events the warp resolves up to 32
 //  of them at once, in stream order.
 //  Phase 1, one event per lane:
 //    - the lane re-runs the filter over the quarters that reported, this time recording which start
 //      positions fired and which bytes are NUL;
-//    - it finds the packet that holds its first candidate by binary search in its item's slice of
-//      `offsets`;
+//    - it finds the packet that holds its first candidate in its item's slice of `offsets` (interpolation
+//      guess, then binary search); the item's packet and byte range waits in the warp's scratch words;
 //    - a candidate start q in packet [ps, pe) is alive when no NUL lies in [ps, q) -- the reference's
 //      "text ends at the first NUL" rule (serial.c:191).  NULs inside the group come from the lane's own
 //      mask; the last NUL before the group comes from the nearest earlier event that held one (events
 //      are in stream order, every NUL byte of the stream raises one) or from the warp's carry.
 //  Phase 2, one alive candidate per lane, whichever event it came from (they are numbered across the
-//  lanes by a prefix sum): it is looked up in the start-anchored hash tables of automaton.c (first
-//  min(len,4) bytes -> pattern records, remaining bytes compared word by word) and counted when it ends
-//  inside its packet (q + len <= pe).
+//  lanes by a prefix sum): its first two bytes select a slot of the verification tables of automaton.c, the
+//  slot's pattern records (first 8 bytes + masks, length, id) are compared, longer patterns word by word,
+//  and a hit is counted when it ends inside its packet (q + len <= pe).
 //  So every pattern occurrence that lies inside one packet and has no NUL before it in that packet is
 //  counted exactly once.  Counts go to shared-memory counters and leave the block as one atomic per
 //  distinct pattern.  No separators, no padding and no second pass over the payload.
