@@ -269,6 +269,29 @@ def test_many_small_packets_and_item_edges(matchers, oracle):
     check_all(matchers, oracle, pats, big + pkts[:100], engines=["union"])
 
 
+def test_nul_dense_payloads(matchers, oracle):
+    """Binary-looking payloads: most 32-byte groups hold a NUL, so the union engine's rows report from many groups
+    and the NUL-only events a later one supersedes are dropped (union_kernel.cu drop_superseded).  What must
+    survive: a candidate is alive iff no NUL lies between its packet's start and itself, whatever was dropped."""
+    rng = random.Random(77)
+    pats = [b"id", b"ack", b"http", b"xy", b"a", b"NOTIFY", b"content-list"]
+    for p_nul, n_pkt, top in [(1.0, 40, 3000), (0.97, 60, 2500), (0.7, 80, 2000), (0.3, 80, 2000), (0.1, 120, 1500)]:
+        pkts = []
+        for _ in range(n_pkt):
+            n = rng.randint(0, top)
+            body = bytearray(0 if rng.random() < p_nul else rng.choice(b"idackhtpxyNOTIFY") for _ in range(n))
+            for _ in range(rng.randint(0, 6)):  # tokens right after packet starts, after NULs and in NUL-free gaps
+                p = rng.choice(pats)
+                if len(p) <= n:
+                    at = rng.choice([0, rng.randrange(0, n - len(p) + 1)])
+                    body[at:at + len(p)] = p
+            pkts.append(bytes(body))
+        check_all(matchers, oracle, pats, pkts, label="p_nul=%g" % p_nul)
+    # a NUL-free packet between all-NUL packets, and packets that start inside a NUL-dense row
+    pkts = [b"\0" * 5000, b"http id ack " * 40, b"\0" * 37, b"idid", b"\0" * 2048, b"x" * 31 + b"http", b"\0" * 999, b"ackack\0ack"]
+    check_all(matchers, oracle, pats, pkts * 7, label="sandwich")
+
+
 # ---- synthetic workloads of BASELINE.json ------------------------------------------------------
 
 def test_synthetic_device_resident_stream(matchers, oracle, strings):
