@@ -8,8 +8,8 @@
 // chunk holds the match's LAST byte.  Per-pattern hits are summed across the warp with
 // __reduce_add_sync, accumulated in shared memory, and leave the block as one atomic per pattern.
 //
-// The payload is re-walked once per pattern, so this engine is bound by shared-memory lookups
-// (~P x 1.3 per byte), not by HBM; it exists as the literal form of the design, as an independent
+// The packet is read from HBM once, by coalesced 16-byte loads (the scan for its first NUL), and re-walked from L1
+// once per pattern, so this engine is bound by shared-memory lookups (~P x 1.3 per byte), not by HBM; it exists as the literal form of the design, as an independent
 // on-device cross-check of the union engine, and for the DFA-shared-memory-pressure sweep
 // (BASELINE config 4).  Pattern sets whose DFAs exceed shared memory are processed in tiles, one
 // launch per tile.
@@ -51,11 +51,38 @@ kmpb_perpat_kernel(const uint8_t *__restrict__ bytes, uint64_t abs_base, const u
         const uint64_t beg = offsets[k];
         const uint32_t len = (uint32_t)(offsets[k + 1] - beg);
         const uint8_t *text = bytes + (beg - abs_base);
-        // the text ends at the first NUL byte (strlen in kmp_matcher, serial.c:191)
+        // The text ends at the first NUL byte (strlen in kmp_matcher, serial.c:191).  Coalesced 16-byte loads from
+        // the 16-byte boundary below the packet's start, four per lane in flight (2 KB per warp trip), so that a
+        // 1400-byte packet is one round trip to memory instead of one per 32 bytes; the warp stops at the first
+        // trip that holds a NUL.  The batch is readable up to the next multiple of 16 (include/kmpb200.h).
+        const uint32_t lead = (uint32_t)((beg - abs_base) & 15u);
+        const uint4 *vec = reinterpret_cast<const uint4 *>(text - lead);
+        const uint32_t nvec = (lead + len + 15u) / 16u;
         uint32_t z = len;
-        for (uint32_t i = lane; i < len; i += 32)
-            if (text[i] == 0) { z = i; break; }
-        const uint32_t n = __reduce_min_sync(0xffffffffu, z);
+        for (uint32_t v0 = 0; v0 < nvec; v0 += 128) {
+            uint4 w[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                const uint32_t v = v0 + 32 * j + lane;
+                w[j] = v < nvec ? __ldg(vec + v) : make_uint4(~0u, ~0u, ~0u, ~0u);
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                const uint32_t v = v0 + 32 * j + lane;
+                const uint32_t ww[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++) {
+                    uint32_t x = ww[q];
+                    const uint32_t at = 16u * v + 4u * q; // position of this word's first byte, from text - lead
+                    if (at < lead) x |= lead - at >= 4 ? ~0u : (1u << (8u * (lead - at))) - 1u; // bytes before the packet
+                    // bit 7 of every byte that is zero (exact per byte: no carries between bytes)
+                    const uint32_t nz = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+                    if (nz) z = min(z, at + ((uint32_t)__ffs(nz) - 1u) / 8u - lead); // at + byte >= lead here
+                }
+            }
+            if (__any_sync(0xffffffffu, z < len)) break;
+        }
+        const uint32_t n = min(len, __reduce_min_sync(0xffffffffu, z));
         if (n == 0) continue;
         const uint32_t chunk = (n + 31) / 32;
         const uint32_t a = lane * chunk;
@@ -104,6 +131,7 @@ int kmpb_launch_perpat(kmpb_ctx *ctx, const kmpb_batch &b, uint64_t *d_uniq_coun
 {
     const kmpb_tables &h = ctx->host;
     if (h.n_uniq == 0 || b.n_packets == 0) return KMPB_OK;
+    if ((uintptr_t)b.d_bytes & 15) return kmpb_fail(KMPB_EINVAL, "payload buffer must be 16-byte aligned"); // 16-byte loads
     const size_t budget = ctx->smem_optin;
     if (!ctx->attr_perpat_set) {
         KMPB_CUDA(cudaFuncSetAttribute(kmpb_perpat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
