@@ -15,7 +15,7 @@ for flags in "$@"; do
   regs=$(grep -A2 "kmpb_union_kernel" $PKG/build/union_kernel.ptxas.log | grep -o "Used [0-9]* registers" | head -1)
   spill=$(grep -A1 "Function properties for _Z17kmpb_union_kernel" $PKG/build/union_kernel.ptxas.log | tail -1 | tr -s ' ')
   if [ -n "$VARIANT_TESTS" ]; then timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -1; fi
-  echo "$(basename $src) $flags | $regs |$spill | $(run)"
+  echo "$(basename $src) $flags | $regs |$spill | $(run) $([ -n "$EXTRA_PY" ] && python $EXTRA_PY 2>&1 | tail -1)"
 done
 cp /tmp/union_kernel.orig.cu $PKG/csrc/cuda/union_kernel.cu
 if [ -n "$BASE" ]; then cp "$BASE" $PKG/libkmpb200.so; echo "BASE again | $(run)"; fi
