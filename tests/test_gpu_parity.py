@@ -332,6 +332,41 @@ def test_synthetic_device_resident_stream(matchers, oracle, strings):
     assert p.count_host(sample, soff) == m.count_host(sample, soff) == oracle.count_csr(sample, soff, strings)
 
 
+def test_sparse_events_over_many_work_items(matchers, oracle):
+    """A batch large enough that every warp of the union engine takes several work items, with events so sparse that
+    a warp's list still holds events of the previous item when the next one starts (and, now and then, of the item
+    before that: the forced resolve).  The per-pattern engine, which knows nothing of items or events, must agree;
+    a prefix is checked against the oracle."""
+    import torch
+
+    n, L = 900_000, 1400  # 1.26 GB: ~19 000 items of 64 KB for 4144 warps
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(99)
+    d_bytes = torch.randint(1, 256, (n * L + 4096,), dtype=torch.uint8, device="cuda:0", generator=g)
+    d_bytes[n * L:].zero_()
+    # a NUL now and then (one packet in ~60): everything behind it in its packet is dead
+    nul_at = torch.randint(0, n * L, (n // 60,), device="cuda:0", generator=g)
+    d_bytes[nul_at] = 0
+    d_off = torch.arange(0, (n + 1) * L, L, dtype=torch.int64, device="cuda:0")
+    pats = [b"\x01\x02", b"ab", b"xyz", b"\xff\xfe\xfd", b"Q"]
+    counts = {}
+    for e in ENGINES:
+        m = matchers[e]
+        m.set_patterns(pats)
+        d_counts = torch.zeros(len(pats), dtype=torch.int64, device="cuda:0")
+        m.count_device(d_bytes.data_ptr(), d_off.data_ptr(), n, d_counts.data_ptr(), span=(0, n * L))
+        torch.cuda.synchronize()
+        counts[e] = d_counts.cpu().tolist()
+    assert counts["union"] == counts["perpat"], counts
+    assert min(counts["union"]) > 0
+    k = 20_000
+    hdata = d_bytes[: k * L].cpu().numpy()
+    hoff = np.arange(0, (k + 1) * L, L, dtype=np.uint64)
+    m = matchers["union"]
+    m.set_patterns(pats)
+    assert m.count_host(hdata, hoff) == oracle.count_csr(hdata, hoff, pats)
+
+
 def test_fused_reduce_into_several_vectors(matchers, oracle, strings):
     """kmpb_count_device_span_peers: the kernel's last block adds the counts to every vector it is given
     (on a multi-GPU box the other vectors are peers' memory; here they are local)."""
