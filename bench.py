@@ -15,8 +15,9 @@ A "step" is one pass of the hot path over the rank's whole slice.
   e2e    the same pass through the C ABI's host entry point kmpb_count_host: pinned host CSR -> chunked
          H2D on 4 streams overlapped with the kernels -> counts back on the host
   roofline      the union kernel alone (events around the kernel on its stream) vs the measured HBM peak
-  cpu_baseline  the unmodified reference (oracle/_ref/openmp_data, all host threads) on a bounded prefix
-                of the same stream -- a reported baseline, not the target
+  cpu_baseline  the unmodified reference on a bounded prefix of the same stream: oracle/_ref/openmp_data on all host
+                threads, and under "serial" oracle/_ref/serial on one core (a shorter prefix) -- reported baselines,
+                not the target
 --impl reference times that CPU program as the step itself.
 """
 import argparse
@@ -195,9 +196,10 @@ def write_pcap(path, data, offsets):
                 f.write(data[int(offsets[k]):int(offsets[k + 1])].tobytes())
 
 
-def run_reference_program(pcap, strings, threads):
-    """oracle/_ref/openmp_data (the unmodified reference, -O2) -> (self-reported seconds, wall seconds, stdout)."""
-    exe = os.path.join(REFBIN, "openmp_data")
+def run_reference_program(pcap, strings, threads, program="openmp_data"):
+    """oracle/_ref/openmp_data or oracle/_ref/serial (the unmodified reference, -O2) -> (self-reported seconds,
+    wall seconds, stdout).  serial.c takes no thread count and times reading the savefile too (serial.c:110-160)."""
+    exe = os.path.join(REFBIN, program)
 
     def unlimited_stack():  # openmp_data.c:123 puts one pointer per packet on the stack
         try:
@@ -207,8 +209,8 @@ def run_reference_program(pcap, strings, threads):
 
     env = {k: v for k, v in os.environ.items() if not k.startswith("MALLOC_")}
     t0 = time.perf_counter()
-    out = subprocess.run([exe, pcap, strings, str(threads)], capture_output=True, env=env, preexec_fn=unlimited_stack,
-                         check=True).stdout
+    argv = [exe, pcap, strings] + ([str(threads)] if program == "openmp_data" else [])
+    out = subprocess.run(argv, capture_output=True, env=env, preexec_fn=unlimited_stack, check=True).stdout
     wall = time.perf_counter() - t0
     lines = out.decode("latin-1").splitlines()
     return float(lines[-1].split("=")[1].split()[0]), wall, "\n".join(lines[:-1]) + "\n"
@@ -520,6 +522,19 @@ def ours(args, kmp, patterns):
             ours_text = kmp.format_report(patterns, d_c.cpu().tolist()).decode("latin-1")
             line["cpu_baseline"] = {"value": n * L / secs / 1e9, "unit": "GB/s", "cores": ref.cores, "kind": ref.kind,
                                     "sample": ref.sample_text(), "seconds": secs, "counts_match_gpu": ours_text == text}
+            if ref.kind == "reference" and os.path.isfile(os.path.join(REFBIN, "serial")):
+                # serial.c, the one-core form of the same loop, on a prefix of that sample sized for a few seconds
+                ns = max(min(n // (2 * ref.cores), n), 1000)
+                spcap = os.path.join(ref.tmp, "serial.pcap")
+                write_pcap(spcap, ref.data[: ns * L], ref.offsets[: ns + 1])
+                ssecs, _, stext = run_reference_program(spcap, os.path.join(DATA, "strings.txt"), 1, program="serial")
+                d_c.zero_()
+                m.count_device(d_bytes.data_ptr(), d_off.data_ptr(), ns, d_c.data_ptr(), span=(0, ns * L), stream=stream.cuda_stream)
+                torch.cuda.synchronize()
+                line["cpu_baseline"]["serial"] = {
+                    "value": ns * L / ssecs / 1e9, "unit": "GB/s", "cores": 1, "seconds": ssecs,
+                    "sample": "first %d packets of the same stream, oracle/_ref/serial -O2 self-reported Elapsed time (includes reading the savefile)" % ns,
+                    "counts_match_gpu": kmp.format_report(patterns, d_c.cpu().tolist()).decode("latin-1") == stext}
             if ref.kind == "reference":
                 # the step before the path: savefile -> pinned CSR batch, on the same sample pcap
                 t0 = time.perf_counter()
