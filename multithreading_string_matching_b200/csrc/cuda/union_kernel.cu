@@ -136,7 +136,32 @@ __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets
     // items, so that the warps run dry within a quarter item of each other at the end of the batch
     const uint64_t target = offsets[0] + (i <= n_big ? (uint64_t)i * item_bytes
                                                      : (uint64_t)n_big * item_bytes + (uint64_t)(i - n_big) * (item_bytes / 4));
+    // guess by the mean packet size (exact for equal-sized packets), bracket the answer by doubling steps around the
+    // guess, then bisect: a few dependent loads instead of log2(n_packets)
+    const uint64_t first = offsets[0], total = offsets[n_packets] - first;
     uint32_t lo = 0, hi = n_packets;
+    if (total) {
+        const double frac = (double)(target - first) / (double)total;
+        uint32_t g = (uint32_t)(frac * (double)n_packets);
+        g = g > n_packets ? n_packets : g;
+        if (offsets[g] < target) { // the answer lies above g
+            lo = g + 1;
+            for (uint32_t step = 1; lo < n_packets; step *= 2) {
+                const uint32_t probe = lo + step - 1 < n_packets ? lo + step - 1 : n_packets;
+                if (offsets[probe] >= target) { hi = probe; break; }
+                lo = probe + 1;
+                if (probe == n_packets) break;
+            }
+            if (lo > hi) lo = hi;
+        } else { // at or below g
+            hi = g;
+            for (uint32_t step = 1; hi > 0; step *= 2) {
+                const uint32_t probe = hi > step ? hi - step : 0;
+                if (offsets[probe] < target) { lo = probe + 1; break; }
+                hi = probe;
+            }
+        }
+    }
     while (lo < hi) {
         uint32_t mid = lo + (hi - lo) / 2;
         if (offsets[mid] < target) lo = mid + 1; else hi = mid;
