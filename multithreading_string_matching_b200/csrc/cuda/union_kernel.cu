@@ -72,7 +72,7 @@ constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item si
 #ifndef KMPB_UN_TAIL_ITEMS
 #define KMPB_UN_TAIL_ITEMS 16384
 #endif
-constexpr uint32_t UN_TAIL_ITEMS = KMPB_UN_TAIL_ITEMS;   // quarter-size items at the end of a batch (about one per warp x 4)
+constexpr uint32_t UN_TAIL_ITEMS = KMPB_UN_TAIL_ITEMS;   // small items at the end of a batch (about one per warp x 4)
 #ifndef KMPB_UN_QCAP
 #define KMPB_UN_QCAP 32
 #endif
@@ -125,17 +125,18 @@ struct union_params {
 
 // ---- work partition: item i = packets [items[i], items[i+1]) ---------------------------------
 __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets, uint32_t n_packets,
-                                            uint32_t n_items, uint32_t n_big, uint64_t item_bytes, uint32_t *__restrict__ items,
+                                            uint32_t n_items, uint32_t n_big, uint64_t item_bytes, uint64_t small_bytes,
+                                            uint32_t *__restrict__ items,
                                             uint32_t *__restrict__ work)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { work[0] = 0; work[1] = 0; work[2] = 0; }
     if (i > n_items) return;
     if (i == n_items) { items[i] = n_packets; return; }
-    // first packet whose start is >= the item's target byte: n_big items of item_bytes, then quarter-size
-    // items, so that the warps run dry within a quarter item of each other at the end of the batch
+    // first packet whose start is >= the item's target byte: n_big items of item_bytes, then small
+    // items, so that the warps run dry within a small item of each other at the end of the batch
     const uint64_t target = offsets[0] + (i <= n_big ? (uint64_t)i * item_bytes
-                                                     : (uint64_t)n_big * item_bytes + (uint64_t)(i - n_big) * (item_bytes / 4));
+                                                     : (uint64_t)n_big * item_bytes + (uint64_t)(i - n_big) * small_bytes);
     // guess by the mean packet size (exact for equal-sized packets), bracket the answer by doubling steps around the
     // guess, then bisect: a few dependent loads instead of log2(n_packets)
     const uint64_t first = offsets[0], total = offsets[n_packets] - first;
@@ -855,13 +856,16 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     // Taking an item costs a warp three dependent trips to L2 (ticket, item table, offsets); large batches
     // afford larger items (C3, 14 GB: 64 KB items 2.96 TB/s, 256 KB items 3.00 TB/s).
     const uint64_t item_bytes = span >= (8ull << 30) ? 4ull * UN_ITEM_BYTES : span >= (4ull << 30) ? 2ull * UN_ITEM_BYTES : UN_ITEM_BYTES;
-    // full-size items, except the last UN_TAIL_ITEMS/4 items' worth of bytes (at most an eighth of the batch),
-    // which is cut into quarter-size items
+    // full-size items, except the last UN_TAIL_ITEMS small items (at most an eighth of the batch), so that the warps
+    // run dry within a few rows of each other at the end of the batch: an eighth of a full item, at least 16 KB
+    // (C3 with 256 KB items: 64 KB tails 3003 GB/s, 32 KB 3013, 16 KB 2995, 8 KB 2985)
+    const uint64_t tail_div = std::min<uint64_t>(8, item_bytes / (UN_ITEM_BYTES / 4));
     const uint64_t whole = span / item_bytes;
-    const uint64_t tail_items = std::min<uint64_t>(UN_TAIL_ITEMS / 4, whole / 8); // at most an eighth of the batch
+    const uint64_t small_bytes = item_bytes / tail_div;
+    const uint64_t tail_items = std::min<uint64_t>(UN_TAIL_ITEMS / tail_div, whole / 8); // at most an eighth of the batch
     const uint32_t n_big = (uint32_t)(whole - tail_items);
     const uint64_t small_span = span - (uint64_t)n_big * item_bytes;
-    const uint32_t n_items = n_big + (uint32_t)((small_span + item_bytes / 4 - 1) / (item_bytes / 4));
+    const uint32_t n_items = n_big + (uint32_t)((small_span + small_bytes - 1) / small_bytes);
     if ((size_t)n_items + 1 > ctx->items_cap) return kmpb_fail(KMPB_ESTATE, "union scratch too small");
     uint32_t *d_items = ctx->d_items + (size_t)slot * ctx->items_cap;
     uint32_t *d_work = ctx->d_work + slot * 4;
@@ -878,7 +882,7 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
         ctx->attr_union_set = true;
     }
     kmpb_union_partition_kernel<<<(n_items + 1 + 255) / 256, 256, 0, stream>>>(b.d_offsets, (uint32_t)b.n_packets, n_items,
-                                                                              n_big, item_bytes, d_items, d_work);
+                                                                              n_big, item_bytes, small_bytes, d_items, d_work);
     union_params p;
     p.bytes = b.d_bytes;
     p.abs_base = b.abs_base;
