@@ -93,30 +93,31 @@ kmpb_perpat_kernel(const uint8_t *__restrict__ bytes, uint64_t abs_base, const u
             const uint32_t m = s_off[t + 1] - s_off[t];
             uint32_t hits = 0;
             if (a < n && n >= m) { // "no point trying to match things", serial.c:193
-                const uint8_t *rows = s_dfa + 256u * s_off[t];
-                uint32_t state = 0;
+                // One DFA step: entry = rows[256 * state + byte] = next state | hit << 7.  `sp` is the shared address of
+                // the current state's row, so a step is: add the byte, load, count bit 7, rebuild the row address.
+                const uint32_t rows = (uint32_t)__cvta_generic_to_shared(s_dfa + 256u * s_off[t]);
+                uint32_t sp = rows;
+                auto step = [&](uint32_t byte) {
+                    uint32_t e;
+                    asm("ld.shared.u8 %0, [%1];" : "=r"(e) : "r"(sp + byte));
+                    hits += e >> 7;
+                    sp = rows + ((e & 0x7fu) << 8);
+                };
+                // run-in: the (m - 1) bytes before my chunk only bring the automaton into its state; a hit there has
+                // its last byte in the previous lane's chunk and is that lane's
                 uint32_t i = a >= m - 1 ? a - (m - 1) : 0;
-                // bytes up to the next word boundary, whole words, then the rest
-                while (i < stop && ((text_addr + i) & 3u)) {
-                    const uint32_t e = rows[256u * state + text[i]];
-                    state = e & 0x7fu;
-                    hits += (e >> 7) & (uint32_t)(i >= a); // a hit belongs to the chunk holding its last byte
-                    i++;
-                }
+                for (; i < a; i++) step(text[i]);
+                hits = 0;
+                // my chunk: bytes up to the next word boundary, whole words (one load per four steps), the rest
+                for (; i < stop && ((text_addr + i) & 3u); i++) step(text[i]);
                 for (; i + 4 <= stop; i += 4) {
                     const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(text + i));
-#pragma unroll
-                    for (uint32_t b = 0; b < 4; b++) {
-                        const uint32_t e = rows[256u * state + ((w >> (8 * b)) & 0xffu)];
-                        state = e & 0x7fu;
-                        hits += (e >> 7) & (uint32_t)(i + b >= a);
-                    }
+                    step(w & 0xffu);
+                    step(__byte_perm(w, 0, 0x4441));
+                    step(__byte_perm(w, 0, 0x4442));
+                    step(w >> 24);
                 }
-                for (; i < stop; i++) {
-                    const uint32_t e = rows[256u * state + text[i]];
-                    state = e & 0x7fu;
-                    hits += (e >> 7) & (uint32_t)(i >= a);
-                }
+                for (; i < stop; i++) step(text[i]);
             }
             const uint32_t total = __reduce_add_sync(0xffffffffu, hits);
             if (lane == 0 && total) atomicAdd(&s_counts[t], total);
