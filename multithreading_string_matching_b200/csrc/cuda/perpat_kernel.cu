@@ -19,6 +19,47 @@
 
 constexpr int PP_THREADS = 1024;
 
+// One lane's walk over its chunk [a, stop) of a text for NP (1 or 2) patterns at once -> hits whose last byte lies in
+// the chunk.  One DFA step: entry = rows[256 * state + byte] = next state | hit << 7; `sp` is the shared address of
+// the current state's row, so a step is: add the byte, load, count bit 7, rebuild the row address.  mm = the longer
+// pattern's length.
+template <int NP>
+__device__ __forceinline__ uint2 walk_chunk(const uint8_t *text, const uint32_t a, const uint32_t stop, const uint32_t mm,
+                                           const uint32_t rows0, const uint32_t rows1)
+{
+    uint32_t sp0 = rows0, sp1 = rows1, hits0 = 0, hits1 = 0;
+    auto step = [&](uint32_t byte) {
+        uint32_t e0, e1 = 0;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(e0) : "r"(sp0 + byte));
+        if (NP == 2) asm("ld.shared.u8 %0, [%1];" : "=r"(e1) : "r"(sp1 + byte));
+        hits0 += e0 >> 7;
+        sp0 = rows0 + ((e0 & 0x7fu) << 8);
+        if (NP == 2) {
+            hits1 += e1 >> 7;
+            sp1 = rows1 + ((e1 & 0x7fu) << 8);
+        }
+    };
+    // run-in: the (m - 1) bytes before the chunk only bring the automaton into its state (a KMP state depends on the
+    // last m - 1 bytes at most, so starting earlier for the shorter pattern changes nothing); a hit there has its last
+    // byte in the previous lane's chunk and is that lane's
+    uint32_t i = a >= mm - 1 ? a - (mm - 1) : 0;
+    for (; i < a; i++) step(text[i]);
+    hits0 = hits1 = 0;
+    // the chunk: bytes up to the next word boundary, whole words (L1-resident after the NUL scan, one load per four
+    // steps), the rest
+    const uintptr_t text_addr = reinterpret_cast<uintptr_t>(text);
+    for (; i < stop && ((text_addr + i) & 3u); i++) step(text[i]);
+    for (; i + 4 <= stop; i += 4) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(text + i));
+        step(w & 0xffu);
+        step(__byte_perm(w, 0, 0x4441));
+        step(__byte_perm(w, 0, 0x4442));
+        step(w >> 24);
+    }
+    for (; i < stop; i++) step(text[i]);
+    return make_uint2(hits0, hits1);
+}
+
 __global__ void __launch_bounds__(PP_THREADS, 1)
 kmpb_perpat_kernel(const uint8_t *__restrict__ bytes, uint64_t abs_base, const uint64_t *__restrict__ offsets,
                    uint64_t n_packets, const uint8_t *__restrict__ dfa_all, const uint32_t *__restrict__ uniq_off,
@@ -87,40 +128,24 @@ kmpb_perpat_kernel(const uint8_t *__restrict__ bytes, uint64_t abs_base, const u
         const uint32_t chunk = (n + 31) / 32;
         const uint32_t a = lane * chunk;
         const uint32_t stop = min(a + chunk, n);
-        // my chunk as aligned 32-bit words (L1-resident after the NUL scan): one load per four DFA steps
-        const uintptr_t text_addr = reinterpret_cast<uintptr_t>(text);
-        for (uint32_t t = 0; t < n_tile; t++) {
-            const uint32_t m = s_off[t + 1] - s_off[t];
-            uint32_t hits = 0;
-            if (a < n && n >= m) { // "no point trying to match things", serial.c:193
-                // One DFA step: entry = rows[256 * state + byte] = next state | hit << 7.  `sp` is the shared address of
-                // the current state's row, so a step is: add the byte, load, count bit 7, rebuild the row address.
-                const uint32_t rows = (uint32_t)__cvta_generic_to_shared(s_dfa + 256u * s_off[t]);
-                uint32_t sp = rows;
-                auto step = [&](uint32_t byte) {
-                    uint32_t e;
-                    asm("ld.shared.u8 %0, [%1];" : "=r"(e) : "r"(sp + byte));
-                    hits += e >> 7;
-                    sp = rows + ((e & 0x7fu) << 8);
-                };
-                // run-in: the (m - 1) bytes before my chunk only bring the automaton into its state; a hit there has
-                // its last byte in the previous lane's chunk and is that lane's
-                uint32_t i = a >= m - 1 ? a - (m - 1) : 0;
-                for (; i < a; i++) step(text[i]);
-                hits = 0;
-                // my chunk: bytes up to the next word boundary, whole words (one load per four steps), the rest
-                for (; i < stop && ((text_addr + i) & 3u); i++) step(text[i]);
-                for (; i + 4 <= stop; i += 4) {
-                    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(text + i));
-                    step(w & 0xffu);
-                    step(__byte_perm(w, 0, 0x4441));
-                    step(__byte_perm(w, 0, 0x4442));
-                    step(w >> 24);
-                }
-                for (; i < stop; i++) step(text[i]);
+        // Two patterns per walk: their automata step on the same text bytes, and two independent chains of
+        // (shared-memory load -> next row address) per lane hide each other's latency.
+        for (uint32_t t = 0; t < n_tile; t += 2) {
+            const bool two = t + 1 < n_tile;
+            const uint32_t m0 = s_off[t + 1] - s_off[t], m1 = two ? s_off[t + 2] - s_off[t + 1] : m0;
+            uint2 hits = make_uint2(0, 0);
+            if (a < n) { // (a pattern longer than the text cannot hit: "no point trying to match things", serial.c:193)
+                const uint32_t rows0 = (uint32_t)__cvta_generic_to_shared(s_dfa + 256u * s_off[t]);
+                const uint32_t rows1 = (uint32_t)__cvta_generic_to_shared(s_dfa + 256u * s_off[two ? t + 1 : t]);
+                const uint32_t mm = m0 > m1 ? m0 : m1;
+                hits = two ? walk_chunk<2>(text, a, stop, mm, rows0, rows1) : walk_chunk<1>(text, a, stop, mm, rows0, rows1);
             }
-            const uint32_t total = __reduce_add_sync(0xffffffffu, hits);
-            if (lane == 0 && total) atomicAdd(&s_counts[t], total);
+            const uint32_t total0 = __reduce_add_sync(0xffffffffu, hits.x);
+            if (lane == 0 && total0) atomicAdd(&s_counts[t], total0);
+            if (two) {
+                const uint32_t total1 = __reduce_add_sync(0xffffffffu, hits.y);
+                if (lane == 0 && total1) atomicAdd(&s_counts[t + 1], total1);
+            }
         }
     }
     __syncthreads();
