@@ -3,48 +3,53 @@
 // This is the reference's packet x pattern double loop (serial.c:153-155) laid out the way
 // BASELINE.json's north_star prescribes: every distinct pattern has a byte-indexed KMP transition
 // DFA (built on the device, tables.cu) staged in shared memory; one warp takes one packet, cuts its
-// text into 32 chunks, and every lane walks its chunk once per pattern, starting (pattern_len-1)
-// bytes early so a match that straddles a chunk edge is seen by exactly one lane -- the one whose
-// chunk holds the match's LAST byte.  Per-pattern hits are summed across the warp with
-// __reduce_add_sync, accumulated in shared memory, and leave the block as one atomic per pattern.
+// text into 32 chunks, and every lane walks its chunk for every pattern (four patterns per walk), starting
+// (pattern_len-1) bytes early so a match that straddles a chunk edge is seen by exactly one lane -- the one whose
+// chunk holds the match's LAST byte.  Per-pattern hits are summed across the warp with __reduce_add_sync,
+// accumulated in shared memory, and leave the block as one atomic per pattern.
 //
 // The packet is read from HBM once, by coalesced 16-byte loads (the scan for its first NUL), and re-walked from L1
-// once per pattern, so this engine is bound by shared-memory lookups (~P x 1.3 per byte), not by HBM; it exists as the literal form of the design, as an independent
-// on-device cross-check of the union engine, and for the DFA-shared-memory-pressure sweep
-// (BASELINE config 4).  Pattern sets whose DFAs exceed shared memory are processed in tiles, one
-// launch per tile.
+// for every group of four patterns, so this engine is bound by instruction issue (~P x 5.5 instructions per byte),
+// not by HBM; it exists as the literal form of the design, as an independent on-device cross-check of the union
+// engine, and for the DFA-shared-memory-pressure sweep (BASELINE config 4).  Pattern sets whose DFAs exceed shared
+// memory are processed in tiles, one launch per tile.
 #include <algorithm>
 
 #include "kmpb_device.cuh"
 
 constexpr int PP_THREADS = 1024;
 
-// One lane's walk over its chunk [a, stop) of a text for NP (1 or 2) patterns at once -> hits whose last byte lies in
-// the chunk.  One DFA step: entry = rows[256 * state + byte] = next state | hit << 7; `sp` is the shared address of
-// the current state's row, so a step is: add the byte, load, count bit 7, rebuild the row address.  mm = the longer
-// pattern's length.
+constexpr int PP_GROUP = 4; // patterns per walk
+
+// One lane's walk over its chunk [a, stop) of a text for NP (1..PP_GROUP) patterns at once -> hits[] whose last byte
+// lies in the chunk.  One DFA step: entry = rows[256 * state + byte] = next state | hit << 7; `sp` is the shared
+// address of the current state's row, so a step is: add the byte, load, count bit 7, rebuild the row address.  The
+// automata step on the same text bytes, and NP independent chains of (shared-memory load -> next row address) per
+// lane hide each other's latency.  mm = the longest pattern's length.
 template <int NP>
-__device__ __forceinline__ uint2 walk_chunk(const uint8_t *text, const uint32_t a, const uint32_t stop, const uint32_t mm,
-                                           const uint32_t rows0, const uint32_t rows1)
+__device__ __forceinline__ void walk_chunk(const uint8_t *text, const uint32_t a, const uint32_t stop, const uint32_t mm,
+                                          const uint32_t (&rows)[PP_GROUP], uint32_t (&hits)[PP_GROUP])
 {
-    uint32_t sp0 = rows0, sp1 = rows1, hits0 = 0, hits1 = 0;
+    uint32_t sp[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) sp[k] = rows[k];
     auto step = [&](uint32_t byte) {
-        uint32_t e0, e1 = 0;
-        asm("ld.shared.u8 %0, [%1];" : "=r"(e0) : "r"(sp0 + byte));
-        if (NP == 2) asm("ld.shared.u8 %0, [%1];" : "=r"(e1) : "r"(sp1 + byte));
-        hits0 += e0 >> 7;
-        sp0 = rows0 + ((e0 & 0x7fu) << 8);
-        if (NP == 2) {
-            hits1 += e1 >> 7;
-            sp1 = rows1 + ((e1 & 0x7fu) << 8);
+        uint32_t e[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) asm("ld.shared.u8 %0, [%1];" : "=r"(e[k]) : "r"(sp[k] + byte));
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            hits[k] += e[k] >> 7;
+            sp[k] = rows[k] + ((e[k] & 0x7fu) << 8);
         }
     };
     // run-in: the (m - 1) bytes before the chunk only bring the automaton into its state (a KMP state depends on the
-    // last m - 1 bytes at most, so starting earlier for the shorter pattern changes nothing); a hit there has its last
+    // last m - 1 bytes at most, so starting earlier for the shorter patterns changes nothing); a hit there has its last
     // byte in the previous lane's chunk and is that lane's
     uint32_t i = a >= mm - 1 ? a - (mm - 1) : 0;
     for (; i < a; i++) step(text[i]);
-    hits0 = hits1 = 0;
+#pragma unroll
+    for (int k = 0; k < NP; k++) hits[k] = 0;
     // the chunk: bytes up to the next word boundary, whole words (L1-resident after the NUL scan, one load per four
     // steps), the rest
     const uintptr_t text_addr = reinterpret_cast<uintptr_t>(text);
@@ -57,7 +62,6 @@ __device__ __forceinline__ uint2 walk_chunk(const uint8_t *text, const uint32_t 
         step(w >> 24);
     }
     for (; i < stop; i++) step(text[i]);
-    return make_uint2(hits0, hits1);
 }
 
 __global__ void __launch_bounds__(PP_THREADS, 1)
@@ -128,23 +132,29 @@ kmpb_perpat_kernel(const uint8_t *__restrict__ bytes, uint64_t abs_base, const u
         const uint32_t chunk = (n + 31) / 32;
         const uint32_t a = lane * chunk;
         const uint32_t stop = min(a + chunk, n);
-        // Two patterns per walk: their automata step on the same text bytes, and two independent chains of
-        // (shared-memory load -> next row address) per lane hide each other's latency.
-        for (uint32_t t = 0; t < n_tile; t += 2) {
-            const bool two = t + 1 < n_tile;
-            const uint32_t m0 = s_off[t + 1] - s_off[t], m1 = two ? s_off[t + 2] - s_off[t + 1] : m0;
-            uint2 hits = make_uint2(0, 0);
+        // PP_GROUP patterns per walk (walk_chunk)
+        for (uint32_t t = 0; t < n_tile; t += PP_GROUP) {
+            const uint32_t np = n_tile - t < (uint32_t)PP_GROUP ? n_tile - t : (uint32_t)PP_GROUP;
+            uint32_t hits[PP_GROUP] = {0, 0, 0, 0};
             if (a < n) { // (a pattern longer than the text cannot hit: "no point trying to match things", serial.c:193)
-                const uint32_t rows0 = (uint32_t)__cvta_generic_to_shared(s_dfa + 256u * s_off[t]);
-                const uint32_t rows1 = (uint32_t)__cvta_generic_to_shared(s_dfa + 256u * s_off[two ? t + 1 : t]);
-                const uint32_t mm = m0 > m1 ? m0 : m1;
-                hits = two ? walk_chunk<2>(text, a, stop, mm, rows0, rows1) : walk_chunk<1>(text, a, stop, mm, rows0, rows1);
+                uint32_t rows[PP_GROUP], mm = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < (uint32_t)PP_GROUP; k++) {
+                    const uint32_t u = t + (k < np ? k : 0);
+                    rows[k] = (uint32_t)__cvta_generic_to_shared(s_dfa + 256u * s_off[u]);
+                    mm = max(mm, s_off[u + 1] - s_off[u]);
+                }
+                if (np == 4) walk_chunk<4>(text, a, stop, mm, rows, hits);
+                else if (np == 3) walk_chunk<3>(text, a, stop, mm, rows, hits);
+                else if (np == 2) walk_chunk<2>(text, a, stop, mm, rows, hits);
+                else walk_chunk<1>(text, a, stop, mm, rows, hits);
             }
-            const uint32_t total0 = __reduce_add_sync(0xffffffffu, hits.x);
-            if (lane == 0 && total0) atomicAdd(&s_counts[t], total0);
-            if (two) {
-                const uint32_t total1 = __reduce_add_sync(0xffffffffu, hits.y);
-                if (lane == 0 && total1) atomicAdd(&s_counts[t + 1], total1);
+#pragma unroll
+            for (uint32_t k = 0; k < (uint32_t)PP_GROUP; k++) {
+                if (k < np) { // warp-uniform
+                    const uint32_t total = __reduce_add_sync(0xffffffffu, hits[k]);
+                    if (lane == 0 && total) atomicAdd(&s_counts[t + k], total);
+                }
             }
         }
     }
