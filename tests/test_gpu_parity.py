@@ -332,6 +332,25 @@ def test_synthetic_device_resident_stream(matchers, oracle, strings):
     assert p.count_host(sample, soff) == m.count_host(sample, soff) == oracle.count_csr(sample, soff, strings)
 
 
+def test_large_pattern_set_tables_in_global_memory(matchers, oracle):
+    """700 patterns of up to 99 bytes: the union engine's verification tables (~100 KB) no longer fit behind the row
+    rings in shared memory and are read from global memory; one- and two-byte patterns and shared prefixes included."""
+    rng = random.Random(4242)
+    alpha = b"abcdefgh01"
+    pats = [bytes(rng.choice(alpha) for _ in range(rng.choice([1, 2, 2, 3, 4, 5, 8, 9, 13, 40, 41, 64, 99]))) for _ in range(700)]
+    pkts = []
+    for _ in range(400):
+        n = rng.choice([0, 3, 40, 100, 700, 1400, 3000])
+        body = bytearray(rng.choice(alpha + b"\0") if rng.random() < 0.02 else rng.choice(alpha) for _ in range(n))
+        for _ in range(rng.randint(0, 4)):
+            p = rng.choice(pats)
+            if len(p) <= n:
+                at = rng.randrange(0, n - len(p) + 1)
+                body[at:at + len(p)] = p
+        pkts.append(bytes(body))
+    check_all(matchers, oracle, pats, pkts, engines=["union"], label="700 patterns")
+
+
 def test_sparse_events_over_many_work_items(matchers, oracle):
     """A batch large enough that every warp of the union engine takes several work items, with events so sparse that
     a warp's list still holds events of the previous item when the next one starts (and, now and then, of the item
