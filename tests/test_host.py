@@ -262,3 +262,22 @@ def test_cli_usage_and_errors(tmp_path):
     assert r.returncode == 1 and "gpu_number" in r.stdout
     r = subprocess.run([exe, os.path.join(DATA, "udp.pcap"), str(tmp_path / "missing.txt")], capture_output=True, text=True)
     assert r.returncode == 1 and r.stderr.startswith("error opening file: ")
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (runs on the host cores, no GPU): exactly one line on stdout, a JSON object with
+    the keys the bench contract names for the reference arm."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-packets", "1500"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "payload_GBps" and d["unit"] == "GB/s" and d["value"] > 0
+    for key in ("n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data"):
+        assert key in d, key
+    assert d["dtype"] == "u8" and d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
