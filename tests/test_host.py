@@ -281,3 +281,49 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_host_side_is_sanitizer_clean(tmp_path):
+    """The C host side (pattern loader, savefile reader, extractors, CSR packer, streamed packer, table builder,
+    report) under AddressSanitizer + UndefinedBehaviorSanitizer over every bundled savefile and over damaged ones
+    (truncated at many lengths, random bytes, empty).  The reference's own loader is not sanitizer-clean (SURVEY.md
+    facts 9-11); ours has to be.  Known answers: SURVEY.md section 4."""
+    exe = str(tmp_path / "test_host_sanitized")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    srcs = [os.path.join(HOSTC, f) for f in ("errors.c", "extract.c", "patterns.c", "pcap_csr.c", "automaton.c")]
+    subprocess.run([cc, "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fopenmp",
+                    "-I" + os.path.join(ROOT, "include"), "-I" + HOSTC, os.path.join(ROOT, "tests", "c", "test_host_sanitized.c")]
+                   + srcs + ["-o", exe], check=True)
+    bundled = [os.path.join(DATA, f) for f in ("udp.pcap", "udp_1000.pcap", "big_udp.pcap", "very_big_udp.pcap", "tcp.pcap")]
+    damaged = []
+    whole = open(os.path.join(DATA, "udp_1000.pcap"), "rb").read()
+    for i, cut in enumerate([0, 1, 23, 24, 25, 39, 40, 41, 100, 1000, len(whole) // 2, len(whole) - 1]):
+        p = tmp_path / ("cut%d.pcap" % i)
+        p.write_bytes(whole[:cut])
+        damaged.append(str(p))
+    rng = np.random.default_rng(5)
+    (tmp_path / "noise.pcap").write_bytes(rng.integers(0, 256, 5000, dtype=np.uint8).tobytes())
+    (tmp_path / "lying.pcap").write_bytes(whole[:24] + struct.pack("<IIII", 0, 0, 0xFFFFFFF0, 0xFFFFFFF0) + whole[40:400])
+    damaged += [str(tmp_path / "noise.pcap"), str(tmp_path / "lying.pcap")]
+    damaged += [str(tmp_path / "noise.pcap"), str(tmp_path / "lying.pcap")]
+    # pcapng: both byte orders and several sections, whole and cut at every eighth byte, and with corrupted block lengths
+    frames = [_udp_frame(b"hello world"), b"short", _udp_frame(b"", ihl=6), _udp_frame(b"x" * 1401), _udp_frame(b"a\0b")]
+    for name, kw in {"le": {}, "be": {"big_endian": True}, "simple": {"simple_from": 2}, "two": {"second_section_at": 3}}.items():
+        ng = _pcapng(frames, **kw)
+        for cut in list(range(0, min(len(ng), 400), 8)) + [len(ng) - 1, len(ng)]:
+            p = tmp_path / ("%s_%d.pcapng" % (name, cut))
+            p.write_bytes(ng[:cut])
+            damaged.append(str(p))
+        for at in (4, 32, 36, 60):
+            bad = bytearray(ng)
+            bad[at:at + 4] = b"\xff\xff\xff\x7f"
+            p = tmp_path / ("%s_bad%d.pcapng" % (name, at))
+            p.write_bytes(bytes(bad))
+            damaged.append(str(p))
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1", OMP_NUM_THREADS="4")
+    r = subprocess.run([exe, os.path.join(DATA, "strings.txt")] + bundled + damaged, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
+    for want in ("udp.pcap udp packets=20 bytes=3347 nulfree=11", "udp_1000.pcap udp packets=321 bytes=84519 nulfree=216",
+                 "big_udp.pcap udp packets=3358 bytes=599424 nulfree=1038", "very_big_udp.pcap udp packets=13768 bytes=1321746 nulfree=0",
+                 "tcp.pcap tcp packets=13 ", "udp_1000.pcap tcp packets=20 "):
+        assert want in r.stdout, (want, r.stdout)
