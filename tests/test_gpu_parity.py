@@ -140,6 +140,14 @@ def test_cli_output_is_the_reference_output(strings):
             assert b"".join(lines[:-1]) == expected, (pcap, argv)
 
 
+def test_integration_snippet_counts(tmp_path):
+    """INTEGRATION.md section 1 as a C program (tests/c/integration_snippet.c): overlapping "aa" in "aaaa" = 3, the
+    text of a payload ends at its NUL."""
+    from test_host import build_integration_snippet
+    r = subprocess.run([build_integration_snippet(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == "aa: 3 times!\nhttp: 3 times!\n", (r.stdout, r.stderr)
+
+
 def test_device_built_prefix_tables(matchers, oracle, strings):
     """kmpb_get_prefix == kmp_prefix (serial.c:217-238): golden vectors + every strings.txt token."""
     vectors = json.load(open(os.path.join(GOLDEN, "kmp_vectors.json")))["vectors"]

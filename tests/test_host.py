@@ -327,3 +327,24 @@ def test_host_side_is_sanitizer_clean(tmp_path):
                  "big_udp.pcap udp packets=3358 bytes=599424 nulfree=1038", "very_big_udp.pcap udp packets=13768 bytes=1321746 nulfree=0",
                  "tcp.pcap tcp packets=13 ", "udp_1000.pcap tcp packets=20 "):
         assert want in r.stdout, (want, r.stdout)
+
+
+def build_integration_snippet(tmp_path):
+    """tests/c/integration_snippet.c (the call sequence of INTEGRATION.md section 1) against include/kmpb200.h and
+    libkmpb200.so only."""
+    exe = str(tmp_path / "integration_snippet")
+    pkg = os.path.join(ROOT, "multithreading_string_matching_b200")
+    subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-O1", "-g", "-Wall", "-Wextra", "-Werror",
+                    "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "integration_snippet.c"),
+                    "-L" + pkg, "-lkmpb200", "-Wl,-rpath," + pkg, "-o", exe], check=True)
+    return exe
+
+
+def test_integration_snippet_links_and_refuses_without_a_device(tmp_path):
+    """The binding a maintainer of serial.c would write compiles warning-free against the public header alone; on a box
+    without a B200 it stops at kmpb_create with the library's message instead of computing on the CPU."""
+    r = subprocess.run([build_integration_snippet(tmp_path)], capture_output=True, text=True)
+    if kmp.lib().kmpb_device_count() > 0:
+        assert r.returncode == 0 and r.stdout == "aa: 3 times!\nhttp: 3 times!\n", (r.stdout, r.stderr)
+    else:
+        assert r.returncode == 1 and "no CPU path" in r.stderr and r.stdout == "", (r.stdout, r.stderr)
