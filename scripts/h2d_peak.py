@@ -1,3 +1,5 @@
+"""Bare pinned host-to-device copy rate of the box (what the end-to-end number of bench.py is bounded by).
+Run on a GPU box: python scripts/h2d_peak.py"""
 import torch, time
 for mb in (64, 256, 1024):
     h = torch.empty(mb << 20, dtype=torch.uint8, pin_memory=True); d = torch.empty_like(h, device="cuda:0")

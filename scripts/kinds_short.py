@@ -1,3 +1,5 @@
+"""Union-kernel rate on 2.8 GB of NUL-free random bytes (no planted tokens): the fast path almost alone.  Printed next
+to every variant by scripts/gpu_variants.sh when EXTRA_PY points here."""
 import sys, os, json
 sys.path.insert(0, ".")
 import numpy as np, torch
