@@ -77,12 +77,12 @@ static double sets_cost(const bucket_sets *s)
     return c;
 }
 
-/* Split the bucket-ordered patterns into <= N_BUCKET contiguous runs minimising the summed
+/* Split the bucket-ordered patterns into <= n_bucket (<= N_BUCKET) contiguous runs minimising the summed
  * per-byte candidate probability.  cut[b]..cut[b+1] is bucket b. */
-static double split_buckets(const pat_ref *sorted, uint32_t n, uint32_t *cut)
+static double split_buckets(const pat_ref *sorted, uint32_t n, uint32_t *cut, uint32_t n_bucket)
 {
-    uint32_t nb = n < N_BUCKET ? n : N_BUCKET;
-    for (uint32_t b = 0; b <= N_BUCKET; b++) cut[b] = n;
+    uint32_t nb = n < n_bucket ? n : n_bucket;
+    for (uint32_t b = 0; b <= n_bucket; b++) cut[b] = n;
     cut[0] = 0;
     if (n == 0) return 0.0;
     if (n > DP_LIMIT) {
@@ -172,9 +172,9 @@ static double bag_cost(const bucket_bag *g)
 
 /* Hill climbing from the contiguous split: move single patterns, then swap pairs, while the summed
  * candidate probability drops.  bucket[i] = bucket of sorted[i]. */
-static double refine_buckets(const pat_ref *sorted, uint32_t n, uint8_t *bucket)
+static double refine_buckets(const pat_ref *sorted, uint32_t n, uint8_t *bucket, uint32_t n_bucket)
 {
-    bucket_bag *bag = calloc(N_BUCKET, sizeof *bag);
+    bucket_bag *bag = calloc(n_bucket, sizeof *bag);
     if (!bag) return -1.0;
     for (uint32_t i = 0; i < n; i++) bag_change(&bag[bucket[i]], &sorted[i], 1);
     for (int sweep = 0, improved = 1; improved && sweep < 64; sweep++) {
@@ -186,7 +186,7 @@ static double refine_buckets(const pat_ref *sorted, uint32_t n, uint8_t *bucket)
             const double gain_out = ca - bag_cost(&bag[a]);
             double best = -1e-15;
             uint32_t to = a;
-            for (uint32_t b = 0; b < N_BUCKET; b++) {
+            for (uint32_t b = 0; b < n_bucket; b++) {
                 if (b == a) continue;
                 const double cb = bag_cost(&bag[b]);
                 bag_change(&bag[b], &sorted[i], 1);
@@ -213,43 +213,76 @@ static double refine_buckets(const pat_ref *sorted, uint32_t n, uint8_t *bucket)
             }
     }
     double total = 0;
-    for (uint32_t b = 0; b < N_BUCKET; b++) total += bag_cost(&bag[b]);
+    for (uint32_t b = 0; b < n_bucket; b++) total += bag_cost(&bag[b]);
     free(bag);
     return total;
 }
 
-static void build_filter(kmpb_tables *t, pat_ref *uniq)
+/* Filter words for n_bucket pattern buckets in fields of field_bits bits: bit (field_bits * d + b) of words[c] is set
+ * when some pattern of bucket b has byte c at depth d (or is shorter than d+1 bytes).  uniq[] is reordered.
+ * Returns the estimated candidate probability per text byte. */
+static double build_filter_words(uint32_t n_uniq, pat_ref *uniq, uint32_t n_bucket, uint32_t field_bits, uint32_t *words)
 {
     uint32_t cut[N_BUCKET + 1];
-    qsort(uniq, t->n_uniq, sizeof *uniq, cmp_bucket);
-    t->filter_fp_estimate = split_buckets(uniq, t->n_uniq, cut);
-    uint8_t *bucket = malloc(t->n_uniq ? t->n_uniq : 1);
-    memset(t->filter, 0, sizeof t->filter);
+    qsort(uniq, n_uniq, sizeof *uniq, cmp_bucket);
+    double estimate = split_buckets(uniq, n_uniq, cut, n_bucket);
+    uint8_t *bucket = malloc(n_uniq ? n_uniq : 1);
+    memset(words, 0, 256 * sizeof *words);
     if (bucket) {
-        for (uint32_t b = 0; b < N_BUCKET; b++)
+        for (uint32_t b = 0; b < n_bucket; b++)
             for (uint32_t i = cut[b]; i < cut[b + 1]; i++) bucket[i] = (uint8_t)b;
-        if (t->n_uniq <= REFINE_LIMIT) {
-            double refined = refine_buckets(uniq, t->n_uniq, bucket);
-            if (refined >= 0) t->filter_fp_estimate = refined;
+        if (n_uniq <= REFINE_LIMIT) {
+            double refined = refine_buckets(uniq, n_uniq, bucket, n_bucket);
+            if (refined >= 0) estimate = refined;
         }
     }
-    for (uint32_t b = 0; b < N_BUCKET; b++) {
+    for (uint32_t b = 0; b < n_bucket; b++) {
         bucket_sets s;
         memset(&s, 0, sizeof s);
         uint32_t members = 0;
-        for (uint32_t i = 0; i < t->n_uniq; i++)
+        for (uint32_t i = 0; i < n_uniq; i++)
             if (bucket ? bucket[i] == b : (i >= cut[b] && i < cut[b + 1])) { sets_add(&s, &uniq[i]); members++; }
         if (members == 0) continue;
         for (uint32_t c = 0; c < 256; c++)
             for (uint32_t d = 0; d < FILTER_DEPTH; d++)
-                if (s.open[d] || (s.set[d][c >> 6] >> (c & 63) & 1)) t->filter[c] |= 1u << (8 * d + b);
+                if (s.open[d] || (s.set[d][c >> 6] >> (c & 63) & 1)) words[c] |= 1u << (field_bits * d + b);
     }
     free(bucket);
+    return estimate;
+}
+
+static void build_filter(kmpb_tables *t, pat_ref *uniq)
+{
+    t->filter_fp_estimate = build_filter_words(t->n_uniq, uniq, N_BUCKET, 8, t->filter);
     /* bucket 7: stages 0..2 always pass, stage 3 passes on NUL only -> bit 31 of the running
      * shift-and word is set exactly on a NUL byte */
     for (uint32_t c = 0; c < 256; c++) t->filter[c] |= 0x00808080u;
     t->filter[0] |= 0x80000000u;
     t->bucket_of_uniq_valid = 1;
+}
+
+/* The same prefilter in the geometry a two-bytes-per-update kernel needs (not used by the
+ * shipped kernels yet): five fields of 6 bits -- depths 0..3 and a fifth field that passes everything, so that a
+ * report lingers one step -- with 5 pattern buckets (bits 0..4 of a field) and the NUL detector in bit 5 (depths
+ * 0..2 always pass, depth 3 passes on NUL only).  One update per byte: S = ((S << 6) | 0x3f) & words[c]; bits 18..22
+ * report the windows that end at this byte, bits 24..28 those that ended at the byte before.  Two bytes per update:
+ *   S = ((S << 12) | 0xfff) & ((words[b0] << 6) | 0x3f) & words[b1]
+ * which is the same function (tests/c/test_tables.c checks it), bits 24..28 then being byte b0's reports. */
+int kmpb_filter6_build(const kmpb_tables *t, uint32_t words[256], double *estimate)
+{
+    pat_ref *uniq = malloc((t->n_uniq ? t->n_uniq : 1) * sizeof *uniq);
+    if (!uniq) return kmpb_fail(KMPB_ENOMEM, "out of memory building the prefilter");
+    for (uint32_t u = 0; u < t->n_uniq; u++) {
+        uniq[u].p = t->uniq_blob + t->uniq_off[u];
+        uniq[u].len = t->uniq_len[u];
+        uniq[u].index = u;
+    }
+    const double e = build_filter_words(t->n_uniq, uniq, 5, 6, words);
+    free(uniq);
+    for (uint32_t c = 0; c < 256; c++) words[c] |= (0x3fu << 24) | (1u << 5) | (1u << 11) | (1u << 17);
+    words[0] |= 1u << 23;
+    if (estimate) *estimate = e;
+    return KMPB_OK;
 }
 
 /* ---- union automaton -------------------------------------------------------------------------- */

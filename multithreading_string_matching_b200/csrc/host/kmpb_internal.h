@@ -75,6 +75,8 @@ void kmpb_pcap_pack(const kmpb_pcap *pc, uint64_t first, uint64_t count, uint8_t
 /* slot of a text position's first two bytes in the verification tables (the device uses the same expression) */
 uint32_t kmpb_vtab_slot(uint32_t first2, uint32_t shift);
 int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat);
+/* the prefilter in 6-bit fields (5 pattern buckets + NUL, depth 4 + a lingering field): automaton.c, DESIGN.md section 10 */
+int kmpb_filter6_build(const kmpb_tables *t, uint32_t words[256], double *estimate);
 void kmpb_tables_free(kmpb_tables *t);
 
 #ifdef __cplusplus

@@ -122,6 +122,36 @@ static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int
             if (!(S & 0x7f000000u)) { fprintf(stderr, "filter missed pattern %d at %d\n", p, s); bad = 1; }
         }
     }
+    /* 2b. the same filter in 6-bit fields (kmpb_filter6_build: 5 buckets + NUL, depth 4 + a lingering field), as a
+     *     two-bytes-per-update kernel would use it: superset of the true occurrences, NUL bit exact, the report of
+     *     the previous byte lingering in bits 24..29, and the two-byte update equal to two one-byte updates */
+    {
+        uint32_t w6[256];
+        double est6 = 0;
+        if (kmpb_filter6_build(&t, w6, &est6) != 0) { fprintf(stderr, "filter6 build failed\n"); return 1; }
+        const uint32_t arm = (1u << 5) | (1u << 11) | (1u << 17), all30 = 0x3fffffffu;
+        for (int p = 0; p < n_pat; p++) {
+            int len = (int)(off[p + 1] - off[p]);
+            for (int s0 = 0; s0 + len <= text_len; s0++) {
+                if (memcmp(text + s0, blob + off[p], (size_t)len)) continue;
+                uint32_t S6 = arm;
+                for (int k = 0; k < 4; k++) S6 = ((S6 << 6) | 0x3fu) & w6[text[s0 + k]]; /* text is zero padded */
+                if (!(S6 & (0x1fu << 18))) { fprintf(stderr, "filter6 missed pattern %d at %d\n", p, s0); bad = 1; }
+            }
+        }
+        uint32_t S1 = arm, S2 = arm;
+        for (int i = 0; i + 1 < text_len; i += 2) {
+            const uint32_t b0 = text[i], b1 = text[i + 1];
+            const uint32_t mid = ((S1 << 6) | 0x3fu) & w6[b0];
+            if (((mid >> 23) & 1u) != (b0 == 0)) { fprintf(stderr, "filter6 NUL bit wrong at %d\n", i); bad = 1; break; }
+            S1 = ((mid << 6) | 0x3fu) & w6[b1];
+            if (((S1 >> 23) & 1u) != (b1 == 0)) { fprintf(stderr, "filter6 NUL bit wrong at %d\n", i + 1); bad = 1; break; }
+            if (((S1 >> 24) & 0x3fu) != ((mid >> 18) & 0x3fu)) { fprintf(stderr, "filter6: report does not linger at %d\n", i); bad = 1; break; }
+            S2 = ((S2 << 12) | 0xfffu) & ((w6[b0] << 6) | 0x3fu) & w6[b1];
+            if ((S1 & all30) != (S2 & all30)) { fprintf(stderr, "filter6: two-byte update differs at %d\n", i); bad = 1; break; }
+        }
+        (void)est6;
+    }
     /* 3. NUL detector */
     uint32_t S = 0x00808080u;
     for (int i = 0; i < text_len; i++) {
