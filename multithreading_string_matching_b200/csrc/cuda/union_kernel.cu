@@ -113,8 +113,9 @@ struct union_params {
     const uint32_t *vtab;    // hash verification tables (automaton.c build_verify_tables)
     uint32_t vtab_words;
     uint32_t vtab_one_off;   // vtab[5]: the one-byte patterns' table, 0 = none
-    uint32_t mul256; // the value 256, passed at run time so the shift-or-0xff compiles to an integer
-                     // multiply-add on the FMA pipe instead of competing for the ALU pipe
+    uint32_t mul256; // the value 256 (64 with KMPB_FILTER6), passed at run time so the shift-or-0xff compiles to an
+                     // integer multiply-add on the FMA pipe instead of competing for the ALU pipe
+    uint32_t mul4096; // KMPB_FILTER6: the two-byte shift
     unsigned long long *uniq_counts;
     // fused expansion + reduction (n_out > 0): the last block to finish adds every pattern's count, in file
     // order, to out[0..n_out) -- this GPU's count vector and/or its peers' (NVLink-mapped)
@@ -259,7 +260,27 @@ __device__ __forceinline__ uint32_t bit_window(uint32_t lo, uint32_t hi)
 #define SEL1 0x7614
 #define SEL2 0x7624
 #define SEL3 0x7634
+#ifdef KMPB_FILTER6
+// Experimental (not the default): the filter in 6-bit fields -- 5 pattern buckets + the NUL
+// detector, depth 4, and a fifth field in which a report lingers one step (automaton.c kmpb_filter6_build) -- so that
+// the row loop updates the state once per TWO bytes: S = ((S << 12) | 0xfff) & G[b0] & L[b1], G = (L << 6) | 0x3f in
+// the second half of the LUT's 256-byte rows.  After the update bits 24..29 are b0's reports, bits 18..23 b1's.
+#define F6_ARM 0x00020820u                                               // NUL stage pre-armed at depths 0..2
+#define LUT_G(word, sel) lds32(__byte_perm((word), lutlane + 128u, (sel)))
+#define SA_NEXT(word, sel) (S = (S * mul + 63u) & LUT_AT(word, sel))     // one byte (the resolve step's re-run)
+#define SA2_STEP(word, selA, selB, acc)                                        \
+    do {                                                                       \
+        S = (S * mul2 + 4095u) & LUT_G(word, selA) & LUT_AT(word, selB);       \
+        acc |= S;                                                              \
+    } while (0)
+#define SA2_WORD(word, acc)               \
+    do {                                  \
+        SA2_STEP(word, SEL0, SEL1, acc);  \
+        SA2_STEP(word, SEL2, SEL3, acc);  \
+    } while (0)
+#else
 #define SA_NEXT(word, sel) (S = (S * mul + 255u) & LUT_AT(word, sel))
+#endif
 #define SA_STEP(word, sel, acc) \
     do {                        \
         SA_NEXT(word, sel);     \
@@ -273,6 +294,18 @@ __device__ __forceinline__ uint32_t bit_window(uint32_t lo, uint32_t hi)
         SA_STEP(word, SEL3, acc); \
     } while (0)
 // same step, shifting "this byte is NUL" into zr (the first step ends up in the highest bit used) ...
+#ifdef KMPB_FILTER6
+#define SZ_STEP(word, sel)                   \
+    do {                                     \
+        SA_NEXT(word, sel);                  \
+        zr = __funnelshift_l(S << 8, zr, 1); \
+    } while (0)
+#define SV_STEP(word, sel)                                              \
+    do {                                                                \
+        SZ_STEP(word, sel);                                             \
+        cmr = __funnelshift_l((S & 0x007c0000u) + 0x7ffc0000u, cmr, 1); \
+    } while (0)
+#else
 #define SZ_STEP(word, sel)                 \
     do {                                   \
         SA_NEXT(word, sel);                \
@@ -284,6 +317,7 @@ __device__ __forceinline__ uint32_t bit_window(uint32_t lo, uint32_t hi)
         SZ_STEP(word, sel);                                             \
         cmr = __funnelshift_l((S & 0x7f000000u) + 0x7f000000u, cmr, 1); \
     } while (0)
+#endif
 #define SV_WORD(word)        \
     do {                     \
         SV_STEP(word, SEL0); \
@@ -417,6 +451,17 @@ __device__ __noinline__ void drain_events(const slow_ctx &c, const uint32_t q_sa
             const uint32_t k8 = (__ffs(quarters) - 1) & ~7u; // 8k
             quarters &= quarters - 1;
             const uint32_t w0 = lds32v(entry_sa + k8), w1 = lds32v(entry_sa + k8 + 4), w2 = lds32v(entry_sa + k8 + 8);
+#ifdef KMPB_FILTER6
+            // quarter k here: bytes 8k..8k+11, starts 8k..8k+8 (the quarters of the row loop overlap by one start;
+            // OR-ing a start bit twice changes nothing)
+            uint32_t S = F6_ARM, cmr = 0, zr = 0;
+            SZ_STEP(w0, SEL0); SZ_STEP(w0, SEL1); SZ_STEP(w0, SEL2);
+            SV_STEP(w0, SEL3);
+            SV_WORD(w1);
+            SV_WORD(w2);
+            cm |= (__brev(cmr) >> 23) << k8;
+            zm |= (__brev(zr) >> 20) << k8;
+#else
             uint32_t S, cmr = 0, zr;
             S = LUT_AT(w0, SEL0) & 0x808080ffu;
             zr = S >> 31;
@@ -426,6 +471,7 @@ __device__ __noinline__ void drain_events(const slow_ctx &c, const uint32_t q_sa
             SV_STEP(w2, SEL0); SV_STEP(w2, SEL1); SV_STEP(w2, SEL2);
             cm |= (__brev(cmr) >> 24) << k8;
             zm |= (__brev(zr) >> 21) << k8;
+#endif
         }
         // the item's first and last rows overhang it: starts count inside [b_abs, e_abs) only, and bytes
         // past e_abs may be stale ring contents, so NULs count below e_abs only
@@ -580,7 +626,15 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     uint32_t *s_vtab = reinterpret_cast<uint32_t *>(ring_all + UN_RING_BYTES); // behind the rings
 
     for (uint32_t i = threadIdx.x; i < 256 * 32; i += UN_THREADS)
+#ifdef KMPB_FILTER6
+    {
+        const uint32_t f = p.filter[i >> 5];
+        reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + (i & 31)] = f;
+        reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + 32 + (i & 31)] = (f << 6) | 0x3fu;
+    }
+#else
         reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + (i & 31)] = p.filter[i >> 5];
+#endif
     if (p.counts_in_smem)
         for (uint32_t i = threadIdx.x; i < p.n_uniq; i += UN_THREADS) s_counts[i] = 0;
     if (p.vtab_in_smem)
@@ -611,6 +665,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     // read back through shared memory so that no LUT load can be scheduled above the barrier
     const uint32_t lutlane = *s_lut_saddr + (lane << 2);
     const uint32_t mul = p.mul256;
+#ifdef KMPB_FILTER6
+    const uint32_t mul2 = p.mul4096;
+#endif
     uint32_t lt;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     const uint32_t q_sa = saddr_of(q_all) + warp * (UN_QCAP * UN_Q_WORDS * 4);
@@ -698,6 +755,26 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             const uint2 la2 = lds64v(UN_TAIL || slot + 1 < UN_SLOTS || lane != 31 ? base + offla : ring_sa);
             const uint32_t la = la2.x;
 
+#ifdef KMPB_FILTER6
+            // ---- shift-and filter over 36 bytes, two per update -----------------------------------
+            // Update j takes bytes 2j, 2j+1 and reports the windows that end there, i.e. the starts 2j-3 and 2j-2.
+            // acc[k] collects the starts 0..8, 9..16, 17..24, 25..31 (k = 0 also the NUL bits of bytes 0..2).
+            uint32_t S = F6_ARM, acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+            SA2_WORD(c0.x, acc0); SA2_WORD(c0.y, acc0); SA2_WORD(c0.z, acc0); // bytes 0..11
+            SA2_WORD(c0.w, acc1); SA2_WORD(c1.x, acc1);                       // bytes 12..19
+            SA2_WORD(c1.y, acc2); SA2_WORD(c1.z, acc2);                       // bytes 20..27
+            SA2_WORD(c1.w, acc3);                                             // bytes 28..31
+            // lookahead: starts 29..31 report here; a NUL here is the next lane's, and so is start 32
+            uint32_t accA = 0, accB = 0;
+            SA2_STEP(la, SEL0, SEL1, accA); // bytes 32, 33: starts 29, 30
+            SA2_STEP(la, SEL2, SEL3, accB); // bytes 34, 35: start 31 (bits 24..28) and start 32
+            acc3 |= (accA & 0x1f7c0000u) | (accB & 0x1f000000u);
+            // a quarter's reports of either byte of an update, merged into bits 18..23; byte 2 of that is
+            // (reports << 2): candidate buckets in bits 2..6, NUL in bit 7 -- the layout the rest of the kernel knows
+            acc0 |= acc0 >> 6; acc1 |= acc1 >> 6; acc2 |= acc2 >> 6; acc3 |= acc3 >> 6;
+            const uint32_t tops =
+                __byte_perm(__byte_perm(acc0, acc1, 0x0062), __byte_perm(acc2, acc3, 0x0062), 0x5410) & 0xfcfcfcfcu;
+#else
             // ---- shift-and filter over 35 bytes ---------------------------------------------------
             // Reports are collected per quarter of the group: acc[k] covers the steps at which starts
             // 8k..8k+7 report (and, for k = 0, the three steps before them, for their NUL bits).
@@ -734,6 +811,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             acc3 |= accC & 0x7f000000u;
             // the four top bytes side by side: quarter k has something to resolve iff byte k is nonzero
             const uint32_t tops = __byte_perm(__byte_perm(acc0, acc1, 0x0073), __byte_perm(acc2, acc3, 0x0073), 0x5410);
+#endif
             const uint32_t m = __ballot_sync(FULL, tops != 0);
 
             // every lane holds its bytes: refill the slot with the row UN_SLOTS ahead
@@ -898,7 +976,13 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     p.vtab = ctx->dev.vtab;
     p.vtab_words = h.vtab_words;
     p.vtab_one_off = h.vtab[5];
+#ifdef KMPB_FILTER6
+    p.mul256 = 64u;
+    p.mul4096 = 4096u;
+#else
     p.mul256 = 256u;
+    p.mul4096 = 0u;
+#endif
     p.uniq_counts = (unsigned long long *)d_uniq_counts;
     p.pat_to_uniq = ctx->dev.pat_to_uniq;
     p.n_pat = h.n_pat;
