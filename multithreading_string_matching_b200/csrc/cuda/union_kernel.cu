@@ -446,7 +446,32 @@ __device__ __noinline__ void drain_events(const slow_ctx &c, const uint32_t q_sa
         // Re-run the filter over the quarters that reported, this time recording which start positions
         // fired and which bytes are NUL.  Quarter k: bytes 8k..8k+10 (three bytes of run-in, then starts
         // 8k..8k+7 report at bytes 8k+3..8k+10); the NUL bit is exact from the first byte on.
-        uint32_t quarters = ((((t.y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t.y) & 0x80808080u); // bit 8k+7: quarter k
+#ifdef KMPB_UN_LEAN_EVENTS
+        // Experimental (not the default, not yet run on a GPU): the row loop pushed only the
+        // group index and the reports; the group's 32 bytes and the 8 after them come from L2 now (the row was read
+        // a few microseconds ago) and go into the event slot, where the rest of the resolve step expects them.
+        // Readable: the batch up to its end rounded up to 32 (include/kmpb200.h); a group at or past the item's end
+        // reported from stale ring bytes and holds nothing of this item.
+        uint32_t reports = t.y;
+        {
+            uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;
+            uint2 g2 = make_uint2(0, 0);
+            if (gq < e_abs) {
+                const uint8_t *src = c.bytes + (uint64_t)UN_GRP * (t.x & 0x7fffffffu);
+                g0 = __ldg(reinterpret_cast<const uint4 *>(src));
+                g1 = __ldg(reinterpret_cast<const uint4 *>(src + 16));
+                if (gq + UN_GRP < e_abs) g2 = __ldg(reinterpret_cast<const uint2 *>(src + 32));
+            } else {
+                reports = 0;
+            }
+            sts128v(entry_sa, g0.x, g0.y, g0.z, g0.w);
+            sts128v(entry_sa + 16, g1.x, g1.y, g1.z, g1.w);
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(entry_sa + 32), "r"(g2.x), "r"(g2.y) : "memory");
+        }
+#else
+        const uint32_t reports = t.y;
+#endif
+        uint32_t quarters = ((((reports & 0x7f7f7f7fu) + 0x7f7f7f7fu) | reports) & 0x80808080u); // bit 8k+7: quarter k
         while (quarters) {
             const uint32_t k8 = (__ffs(quarters) - 1) & ~7u; // 8k
             quarters &= quarters - 1;
@@ -835,9 +860,13 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                         if (qn + n2 > UN_QCAP) resolve_pending();
                         if (tops2 != 0) {
                             const uint32_t e = q_sa + (qn + __popc(m2 & lt)) * (UN_Q_WORDS * 4);
+#ifdef KMPB_UN_LEAN_EVENTS
+                            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(e + 40), "r"(g32 + (r << 5)), "r"(tops2) : "memory");
+#else
                             sts128v(e, c0.x, c0.y, c0.z, c0.w);
                             sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
                             sts128v(e + 32, la, la2.y, g32 + (r << 5), tops2);
+#endif
                         }
                         qn += n2;
                         return;
@@ -846,9 +875,13 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                 }
                 if (tops != 0) {
                     const uint32_t e = q_sa + (qn + __popc(m & lt)) * (UN_Q_WORDS * 4);
+#ifdef KMPB_UN_LEAN_EVENTS
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(e + 40), "r"(g32 + (r << 5)), "r"(tops) : "memory");
+#else
                     sts128v(e, c0.x, c0.y, c0.z, c0.w);
                     sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
                     sts128v(e + 32, la, la2.y, g32 + (r << 5), tops);
+#endif
                 }
                 qn += n;
             }

@@ -10,7 +10,7 @@ for flags in "$@"; do
   src=/tmp/union_kernel.orig.cu
   case "$flags" in SRC=*) src="${flags%% *}"; src="${src#SRC=}"; flags="${flags#SRC=* }"; [ "$flags" = "SRC=$src" ] && flags="";; esac
   cp "$src" $PKG/csrc/cuda/union_kernel.cu
-  rm -f $PKG/build/union_kernel.o $PKG/libkmpb200.so
+  rm -f $PKG/build/union_kernel.o $PKG/build/tables.o $PKG/libkmpb200.so  # tables.cu uploads the filter words (KMPB_FILTER6)
   make -s -C $PKG EXTRA_NVFLAGS="$flags" >/dev/null 2>&1 || { echo "BUILD FAILED: $src $flags"; continue; }
   regs=$(grep -A2 "kmpb_union_kernel" $PKG/build/union_kernel.ptxas.log | grep -o "Used [0-9]* registers" | head -1)
   spill=$(grep -A1 "Function properties for _Z17kmpb_union_kernel" $PKG/build/union_kernel.ptxas.log | tail -1 | tr -s ' ')
