@@ -682,6 +682,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     const uint32_t off0 = lane * UN_GRP, off1 = off0 + 16, offla = off0 + UN_GRP;
 #else
     const uint32_t off0 = lane * UN_GRP + ((lane >> 2) & 1u) * 16, off1 = off0 ^ 16u;
+#ifdef KMPB_UN_COALESCED_COPY
+    const uint32_t coff = (lane * 16) ^ (((lane >> 3) & 1u) << 4); // slot offset of row bytes [16 lane, 16 lane + 16)
+#endif
     // lane 31's lookahead: the slot's tail, or (three slots) the first bytes of the following slot
     const uint32_t offla = lane == 31 ? UN_ROW : (lane + 1) * UN_GRP + (((lane + 1) >> 2) & 1u) * 16;
 #endif
@@ -740,7 +743,11 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sc.scratch_sa + 192), "r"(par), "r"(qn ? 1u : 0u) : "memory");
         }
         const uint64_t row0 = b_abs & ~127ull; // absolute position of the item's first row
+#ifdef KMPB_UN_COALESCED_COPY
+        const uint8_t *textl = p.bytes + (row0 - p.abs_base) + lane * 16; // the 16 bytes of the first row I copy first
+#else
         const uint8_t *textl = p.bytes + (row0 - p.abs_base) + lane * UN_GRP; // my 32 bytes of the item's first row
+#endif
         const uint32_t e_rel = (uint32_t)(e_abs - row0);
         const uint32_t load_end = (e_rel + 15u) & ~15u;
         const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
@@ -752,6 +759,30 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         // that "all but the newest UN_SLOTS-1 groups are complete" always means "the row about to be
         // scanned has arrived".  (A chunk-major slot layout, free of bank conflicts on both sides, measured
         // 14 % slower on the fast path alone.)
+#ifdef KMPB_UN_COALESCED_COPY
+        // Which lane copies which 16 bytes is free (the slot is read after a warp barrier): each copy instruction
+        // moves 512 CONTIGUOUS bytes -- lane l the bytes [16 l, 16 l + 16) of the row's first and of its second half --
+        // instead of every other 16-byte piece.  The per-instruction counters of the capture in profiles/ show why: the
+        // strided form costs 14 shared-memory wavefronts per copy instruction instead of 4 (the data arrives by
+        // 32-byte sectors of which half is used) and fetches every sector of the row twice from L2.  The byte at row
+        // offset x still lands at slot offset x ^ (((x >> 7) & 1) << 4), so nothing else changes.
+        auto issue_row = [&](uint32_t r, uint32_t slot) {
+            const uint32_t row = r * UN_ROW;
+            const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES;
+            const uint8_t *src = add_wide(textl, row); // textl: 16 bytes per lane in this form
+            if (row + UN_SLOT_BYTES <= load_end) {
+                cp_async16(dst + coff, src);
+                cp_async16(dst + coff + 512, src + 512);
+                if (UN_TAIL) cp_async16_if(lane == 31, dst + offtail, src + (UN_ROW - 16 * 31));
+            } else if (row < e_rel) { // r < nrows
+                const uint32_t x = row + lane * 16;
+                if (x < load_end) cp_async16(dst + coff, src);
+                if (x + 512 < load_end) cp_async16(dst + coff + 512, src + 512);
+                if (UN_TAIL && lane == 31 && row + UN_ROW < load_end) cp_async16(dst + offtail, src + (UN_ROW - 16 * 31));
+            }
+            cp_async_commit();
+        };
+#else
         auto issue_row = [&](uint32_t r, uint32_t slot) {
             const uint32_t row = r * UN_ROW;
             const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES;
@@ -768,6 +799,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             }
             cp_async_commit();
         };
+#endif
         for (uint32_t r = 0; r < UN_SLOTS; r++) issue_row(r, r);
 
         // one row: wait for its slot, filter, refill the slot, push the events
