@@ -83,16 +83,7 @@ int kmpb_upload_tables(kmpb_ctx *ctx)
     if ((rc = upload(&d.uniq_len, h.uniq_len, h.n_uniq, s))) return rc;
     if ((rc = upload(&d.pat_to_uniq, h.pat_to_uniq, h.n_pat, s))) return rc;
     if ((rc = upload(&d.vtab, h.vtab, (size_t)h.vtab_words, s))) return rc;
-#ifdef KMPB_FILTER6 // experimental union kernel (union_kernel.cu): the prefilter in 6-bit fields
-    {
-        uint32_t words6[256];
-        if ((rc = kmpb_filter6_build(&h, words6, nullptr))) return rc;
-        if ((rc = upload(&d.filter, words6, 256, s))) return rc;
-        KMPB_CUDA(cudaStreamSynchronize(s)); // words6 is on this stack frame
-    }
-#else
-    if ((rc = upload(&d.filter, h.filter, 256, s))) return rc;
-#endif
+    if ((rc = upload(&d.filter, h.filter6, 256, s))) return rc;
     KMPB_CUDA(cudaMalloc((void **)&d.pi, (blob_len ? blob_len : 1) * sizeof(int32_t)));
     KMPB_CUDA(cudaMalloc((void **)&d.perpat_dfa, blob_len ? blob_len * 256 : 1));
     // per stream slot: distinct-pattern accumulators

@@ -3,45 +3,50 @@
 // Two levels, strictly separated.
 //
 //  FAST PATH (every byte) knows nothing about packets.  A warp streams work items -- runs of whole
-//  packets, ~64 KB of the flat CSR byte buffer -- in rows of 1024 contiguous bytes.  Rows travel
-//  global -> shared memory by per-lane 16-byte asynchronous copies (cp.async, SASS LDGSTS) into a
-//  per-warp ring of UN_SLOTS slots, one commit group per row; a slot holds the row plus the 16 bytes
-//  after it, so every lane finds its lookahead in its own slot.  Each lane pushes its 32 bytes (+3
-//  bytes of lookahead) through a 4-byte-deep shift-and filter over 8 buckets:
-//      S = ((S << 8) | 0xff) & filter[byte]
-//  filter[] lives in shared memory in a bank-private layout (byte address = byte*256 + lane*4) at a
-//  64 KB-aligned shared address, so the one lookup per byte never bank-conflicts and its complete
-//  address is a single PRMT of the text word with a per-lane constant.  The shift-or-0xff is one
-//  integer multiply-add (FMA pipe), the AND one LOP3 (ALU pipe).  Bits 24..30 of S say "the last 4
-//  bytes are the first 4 bytes (or all the bytes) of some pattern of bucket b"; bit 31 says "this
-//  byte is NUL".  The reports are OR-ed per quarter of the group (8 start positions); a lane with any
-//  report appends an EVENT -- its 32 bytes and the 8 after them, where they are, and which quarters reported -- to
-//  the warp's list in shared memory.  That is all: one ballot and (usually) a few stores per row on top of the
-//  filter.  (When the list is full and a row reports from many groups -- NUL-dense payloads -- events that hold
-//  only NULs and are superseded by a later one of the same row are dropped first: drop_superseded.)
+//  packets, ~64 KB of the flat CSR byte buffer -- in rows of 1024 contiguous bytes.  A row travels
+//  global -> registers by ONE coalesced 256-bit load per lane (SASS LDG.E.256, L1 not allocated): lane l
+//  holds bytes [32 l, 32 l + 32) of the row in eight registers; UN_NBUF such row buffers rotate (the loop is
+//  unrolled UN_NBUF times, so the rotation costs no moves) and an L2 prefetch runs UN_PF rows ahead of the
+//  loads.  The four bytes a lane needs after its own come from the next lane's first register (one SHFL); lane
+//  31 loads the eight bytes after the row itself.  (Round 1 staged the rows in a shared-memory ring filled by
+//  cp.async: ring write + read-back cost 17-28 shared-memory wavefronts per row next to the filter's 35.)
+//  Each lane pushes its 32 bytes (+4 bytes of lookahead) through a 4-byte-deep shift-and filter over 5 pattern
+//  buckets and a NUL detector, in 6-bit fields with a fifth field in which a report lingers one step, so that
+//  the state is updated once per TWO bytes:
+//      S = ((S << 12) | 0xfff) & G[b0] & L[b1],      G[c] = (L[c] << 6) | 0x3f
+//  L and G live in shared memory in a bank-private layout (byte address = byte * 128 + lane * 4), so the one
+//  lookup per byte never bank-conflicts; its address is one IDP.4A (byte x 128 + lane base: the FMA pipe, which
+//  this integer kernel otherwise leaves idle; round 1 built the address with a PRMT on the ALU pipe, the busiest
+//  one, and needed a 64 KB-aligned table for it).  The shift-or is one integer multiply-add (FMA pipe), the
+//  three-way AND one LOP3 (ALU pipe).  After an update bits 24..28 say "the 4 bytes ending at b0 are the first 4
+//  bytes (or all the bytes) of some pattern of bucket b", bits 18..22 the same for b1; bits 29 / 23 say "the
+//  byte three before b0 / b1 is NUL" (the NUL detector reports as late as a pattern that starts at the NUL
+//  would, which keeps "what starts here" and "is this a NUL" of a byte in the same report).  The reports are
+//  OR-ed per quarter of the group (8 start positions); a lane with any report appends an EVENT -- its 32 bytes
+//  and the 8 after them, where they are, and which quarters reported -- to the warp's list in shared memory; a
+//  lane with two reporting quarters appends two events, one per quarter, so that the resolve step re-examines
+//  one quarter per event.  That is all: two ballots and (usually) a few stores per row on top of the filter.
+//  (NUL-dense rows: events that hold only NULs and are superseded by a later one of the same row are dropped
+//  first, drop_superseded.)
 //
-//  SLOW PATH (events only).  When the list cannot take the next row's events the warp resolves up to 32
-//  of them at once, in stream order.
-//  Phase 1, one event per lane:
-//    - the lane re-runs the filter over the quarters that reported, this time recording which start
-//      positions fired and which bytes are NUL;
+//  SLOW PATH (events only).  The list is a ring of UN_QCAP slots; whenever it holds 32 events, the warp -- after
+//  it has issued the loads of the next rows -- resolves the 32 oldest at once, in stream order, one per lane:
+//  Phase 1:
+//    - the lane re-runs the filter over the quarter that reported, this time recording which start positions
+//      fired and which bytes are NUL;
 //    - it finds the packet that holds its first candidate in its item's slice of `offsets` (interpolation
 //      guess, then binary search); the item's packet and byte range waits in the warp's scratch words;
 //    - a candidate start q in packet [ps, pe) is alive when no NUL lies in [ps, q) -- the reference's
-//      "text ends at the first NUL" rule (serial.c:191).  NULs inside the group come from the lane's own
-//      mask; the last NUL before the group comes from the nearest earlier event that held one (events
-//      are in stream order, every NUL byte of the stream raises one) or from the warp's carry.
-//  Phase 2, one alive candidate per lane, whichever event it came from (they are numbered across the
-//  lanes by a prefix sum): its first two bytes select a slot of the verification tables of automaton.c, the
-//  slot's pattern records (first 8 bytes + masks, length, id) are compared, longer patterns word by word,
-//  and a hit is counted when it ends inside its packet (q + len <= pe).
+//      "text ends at the first NUL" rule (serial.c:191).  NULs inside the quarter come from the lane's own
+//      mask; the last NUL before it comes from the nearest earlier event that held one (events are in
+//      stream order, every NUL byte of the stream raises one) or from the warp's carry.
+//  Phase 2, every lane its own alive candidates: the candidate's first bytes select one slot in each of the two
+//  probe tables of automaton.c (two-byte patterns by their two bytes, longer ones by their first three), the
+//  slots' pattern records (first 8 bytes + masks, length, id) are compared, longer patterns word by word, and a
+//  hit is counted when it ends inside its packet (q + len <= pe).
 //  So every pattern occurrence that lies inside one packet and has no NUL before it in that packet is
 //  counted exactly once.  Counts go to shared-memory counters and leave the block as one atomic per
 //  distinct pattern.  No separators, no padding and no second pass over the payload.
-//
-//  Measured and dropped: a TMA bulk-copy ring (1 KB cp.async.bulk per row, 3 % slower:
-//  ~25 instructions per row to issue one copy from one elected lane), direct 16-byte loads with an L2
-//  prefetch (10 % slower: exposed latency), 64 bytes per lane (17 % slower), a chunk-major slot layout.
 #include <algorithm>
 
 #include "kmpb_device.cuh"
@@ -52,51 +57,50 @@
 #ifndef KMPB_UN_ITEM_KB
 #define KMPB_UN_ITEM_KB 64
 #endif
-#ifndef KMPB_UN_SLOTS
-#define KMPB_UN_SLOTS 2
+#ifndef KMPB_UN_NBUF
+#define KMPB_UN_NBUF 2
+#endif
+#ifndef KMPB_UN_PF
+#define KMPB_UN_PF 6
 #endif
 constexpr int UN_THREADS = KMPB_UN_THREADS; // one block per SM
 constexpr int UN_WARPS = UN_THREADS / 32;
 constexpr uint32_t UN_GRP = 32;                           // bytes per lane per row
 constexpr uint32_t UN_ROW = 32 * UN_GRP;                  // bytes per warp row
-constexpr uint32_t UN_SLOTS = KMPB_UN_SLOTS;              // rows in flight per warp (cp.async -> shared memory)
-// KMPB_UN_SLOTS == 2: a slot holds a row and the 16 bytes after it (lane 31's lookahead, copied by lane 31).
-// KMPB_UN_SLOTS == 3: a slot holds a row; two rows are complete when a row is scanned, and lane 31 finds its
-// lookahead at the start of the next slot (no tail copy).
-#ifndef KMPB_UN_TAIL
-#define KMPB_UN_TAIL (KMPB_UN_SLOTS < 3)
-#endif
-constexpr bool UN_TAIL = KMPB_UN_TAIL;
-constexpr uint32_t UN_SLOT_BYTES = UN_ROW + (UN_TAIL ? 16 : 0);
+constexpr uint32_t UN_NBUF = KMPB_UN_NBUF;                // row buffers (registers) per lane: UN_NBUF - 1 rows in flight
+constexpr uint32_t UN_PF = KMPB_UN_PF;                    // rows the L2 prefetch runs ahead of the loads (0: none)
+static_assert(UN_NBUF >= 2 && UN_NBUF <= 4, "2..4 row buffers");
 constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item size
 #ifndef KMPB_UN_TAIL_ITEMS
 #define KMPB_UN_TAIL_ITEMS 16384
 #endif
 constexpr uint32_t UN_TAIL_ITEMS = KMPB_UN_TAIL_ITEMS;   // small items at the end of a batch (about one per warp x 4)
-#ifndef KMPB_UN_QCAP
-#define KMPB_UN_QCAP 32
-#endif
-constexpr uint32_t UN_QCAP = KMPB_UN_QCAP;                          // events per warp list
-constexpr uint32_t UN_Q_WORDS = 12; // event: 32 B group, 8 B lookahead, group index | item parity << 31, quarter reports (48 B)
+constexpr uint32_t UN_QCAP = 64;    // slots of a warp's event ring (fewer than 32 pending + at most 32 of a row)
+constexpr uint32_t UN_QDRAIN = 32;  // events resolved at once (one per lane)
+constexpr uint32_t UN_Q_WORDS = 12; // event: 32 B group, 4 B lookahead, -, group index | item parity << 31, quarter reports (48 B)
+constexpr uint32_t UN_Q_BYTES1 = UN_Q_WORDS * 4;
 #ifndef KMPB_UN_DENSE
 #define KMPB_UN_DENSE 8
 #endif
 constexpr uint32_t UN_DENSE = KMPB_UN_DENSE; // reporting groups per row from which superseded NUL-only events are dropped (> 32: never)
-constexpr uint32_t UN_LUT_BYTES = 256 * 256; // 256-byte row per byte value; lanes use the first 128 B
+constexpr uint32_t UN_LUT_BYTES = 256 * 128; // one table: a 128-byte row (32 lanes x 4 bytes) per byte value
 constexpr uint32_t FULL = 0xffffffffu;
 
-// Dynamic shared memory.  The LUT must start at a 64 KB-aligned shared address; the gap in front of it
-// (63 KB when the dynamic window starts at 0x400, the usual case) holds the event lists and the counters;
-// the per-warp row rings follow the LUT, the verification tables follow the rings (as long as they fit).
-constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_WORDS * 4;
-constexpr uint32_t UN_RING_BYTES = UN_WARPS * UN_SLOTS * UN_SLOT_BYTES;
-constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 256;
-constexpr uint32_t UN_FRONT_FIXED = UN_Q_BYTES + UN_SCRATCH_BYTES + 16;
-constexpr uint32_t UN_FRONT_MAX = 60 * 1024; // what the gap is trusted to hold
-constexpr size_t UN_SMEM_BYTES = 65536 + UN_LUT_BYTES + UN_RING_BYTES;
-static_assert(UN_FRONT_FIXED + 1024 <= UN_FRONT_MAX, "event lists do not fit in front of the LUT");
+// Dynamic shared memory: L, G, the event rings, the warps' scratch words, the counters (if they fit), the probe
+// tables (if they fit).
+constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_BYTES1;
+constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
+constexpr uint32_t UN_OFF_Q = 2 * UN_LUT_BYTES;
+constexpr uint32_t UN_OFF_SCRATCH = UN_OFF_Q + UN_Q_BYTES;
+constexpr uint32_t UN_OFF_MISC = UN_OFF_SCRATCH + UN_SCRATCH_BYTES; // 16 bytes: the "I am the last block" flag
+constexpr uint32_t UN_OFF_COUNTS = UN_OFF_MISC + 16;
+constexpr size_t UN_SMEM_FIXED = UN_OFF_COUNTS;
 constexpr size_t UN_SMEM_MAX = 227 * 1024; // opt-in shared memory of one block on sm_100
-static_assert(UN_SMEM_BYTES <= UN_SMEM_MAX, "shared memory budget");
+static_assert(UN_SMEM_FIXED + 16384 <= UN_SMEM_MAX, "shared memory budget");
+
+// the filter's geometry (automaton.c kmpb_filter6_build): fields of 6 bits, bits 0..4 the pattern buckets, bit 5 the NUL
+// detector; after a two-byte update b0's reports sit in bits 24..29, b1's in bits 18..23
+constexpr uint32_t F6_HI = 0x3f000000u, F6_LO = 0x00fc0000u;
 
 struct union_params {
     const uint8_t *bytes; // device pointer to absolute byte abs_base (abs_base % 512 == 0)
@@ -105,17 +109,16 @@ struct union_params {
     uint32_t n_packets;
     const uint32_t *items; // [n_items+1] first packet of each work item
     uint32_t n_items;
-    uint32_t *work;         // [0] next item, [1] error flags
-    const uint32_t *filter; // [256]
+    uint32_t *work;         // [0] next item, [1] error flags, [2] blocks that have finished
+    const uint32_t *filter; // [256] filter words in 6-bit fields
     uint32_t n_uniq;
     uint32_t counts_in_smem; // counters live in shared memory
-    uint32_t vtab_in_smem;   // the hash verification tables live in shared memory
-    const uint32_t *vtab;    // hash verification tables (automaton.c build_verify_tables)
+    uint32_t vtab_in_smem;   // the probe tables live in shared memory
+    const uint32_t *vtab;    // probe tables (automaton.c build_verify_tables); the header words follow as scalars
     uint32_t vtab_words;
-    uint32_t vtab_one_off;   // vtab[5]: the one-byte patterns' table, 0 = none
-    uint32_t mul256; // the value 256 (64 with KMPB_FILTER6), passed at run time so the shift-or-0xff compiles to an
-                     // integer multiply-add on the FMA pipe instead of competing for the ALU pipe
-    uint32_t mul4096; // KMPB_FILTER6: the two-byte shift
+    uint32_t vt_slots_a, vt_shift_a, vt_slots_b, vt_shift_b, vt_one, vt_rec, vt_blob;
+    uint32_t mul64, mul4096; // the values 64 and 4096, passed at run time so that the shift-ors compile to integer
+                             // multiply-adds on the FMA pipe instead of competing for the ALU pipe
     unsigned long long *uniq_counts;
     // fused expansion + reduction (n_out > 0): the last block to finish adds every pattern's count, in file
     // order, to out[0..n_out) -- this GPU's count vector and/or its peers' (NVLink-mapped)
@@ -172,10 +175,33 @@ __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets
 }
 
 // ---- helpers -----------------------------------------------------------------------------------
-// per-lane 16-byte asynchronous copies global -> shared (SASS LDGSTS), completion by commit groups
-__device__ __forceinline__ void cp_async16(uint32_t dst_sa, const void *src)
+// One row buffer of a lane: its 32 bytes of a row and -- meaningful in lane 31 only -- the 4 bytes after the row.
+struct row_regs {
+    uint32_t w[8];
+    uint32_t la;
+};
+// 32 bytes global -> registers in one instruction (SASS LDG.E.256, sm_100), L1 not allocated (the row is used once),
+// under a predicate; a lane that does not load keeps what its registers held (an older row of the same item,
+// or zeros): whatever it reports from them lies past the item's end and is cut by the resolve step
+__device__ __forceinline__ void ldg256_if(bool on, row_regs &b, const void *src)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa), "l"(src) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
+                 "@p ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+                 : "+r"(b.w[0]), "+r"(b.w[1]), "+r"(b.w[2]), "+r"(b.w[3]), "+r"(b.w[4]), "+r"(b.w[5]), "+r"(b.w[6]), "+r"(b.w[7])
+                 : "l"(src), "r"((uint32_t)on));
+}
+// 4 bytes under a predicate (lane 31's lookahead)
+__device__ __forceinline__ void ldg32_if(bool on, uint32_t &v, const void *src)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t"
+                 "@p ld.global.L1::no_allocate.u32 %0, [%1];\n\t}"
+                 : "+r"(v)
+                 : "l"(src), "r"((uint32_t)on));
+}
+// the 128-byte line at src on its way into L2 (SASS CCTL.E.PF2): no registers, no wait
+__device__ __forceinline__ void prefetch_l2_if(bool on, const void *src)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p prefetch.global.L2 [%0];\n\t}" ::"l"(src), "r"((uint32_t)on) : "memory");
 }
 // pointer + 32-bit offset as IMAD.WIDE.U32 (FMA pipe), not IADD3 + IADD3.X (ALU pipe)
 __device__ __forceinline__ const uint8_t *add_wide(const uint8_t *base, uint32_t offset)
@@ -183,18 +209,6 @@ __device__ __forceinline__ const uint8_t *add_wide(const uint8_t *base, uint32_t
     uint64_t r;
     asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(offset), "l"(reinterpret_cast<uint64_t>(base)));
     return reinterpret_cast<const uint8_t *>(r);
-}
-// the same under a predicate (no branch around a single copy)
-__device__ __forceinline__ void cp_async16_if(bool on, uint32_t dst_sa, const void *src)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p cp.async.cg.shared.global [%1], [%2], 16;\n\t}"
-                 ::"r"((uint32_t)on), "r"(dst_sa), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ uint4 lds128v(uint32_t saddr)
 {
@@ -209,16 +223,16 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ uint32_t lds8v(uint32_t saddr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
 __device__ __forceinline__ uint2 lds64(uint32_t saddr)
 {
     uint2 v;
     asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr)
+{
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
     return v;
 }
 __device__ __forceinline__ uint2 lds64v(uint32_t saddr)
@@ -230,18 +244,20 @@ __device__ __forceinline__ uint2 lds64v(uint32_t saddr)
 __device__ __forceinline__ uint32_t lds32v(uint32_t saddr)
 {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
     return v;
+}
+__device__ __forceinline__ void sts32v(uint32_t saddr, uint32_t a)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts64v(uint32_t saddr, uint32_t a, uint32_t b)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void sts128v(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// 4 text bytes starting at byte `pos` of an event (pos + 4 <= 40)
-__device__ __forceinline__ uint32_t entry_window(uint32_t entry_sa, uint32_t pos)
-{
-    const uint32_t a = entry_sa + (pos & ~3u);
-    return __funnelshift_r(lds32v(a), lds32v(a + 4), 8u * (pos & 3u));
 }
 __device__ __forceinline__ uint32_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -252,144 +268,103 @@ __device__ __forceinline__ uint32_t bit_window(uint32_t lo, uint32_t hi)
     const uint32_t below_lo = lo >= 32 ? FULL : (1u << lo) - 1u;
     return below_hi & ~below_lo;
 }
+// x clamped to 0..32, x signed
+__device__ __forceinline__ uint32_t clamp32(int32_t x) { return (uint32_t)min(max(x, 0), 32); }
 
-// filter word of byte `sel` of `word`: the PRMT builds the whole shared address
-// [lutlane.b0 | byte | lutlane.b2 | lutlane.b3], lutlane = 64 KB-aligned LUT base + 4*lane
-#define LUT_AT(word, sel) lds32(__byte_perm((word), lutlane, (sel)))
-#define SEL0 0x7604
-#define SEL1 0x7614
-#define SEL2 0x7624
-#define SEL3 0x7634
-#ifdef KMPB_FILTER6
-// Experimental (not the default): the filter in 6-bit fields -- 5 pattern buckets + the NUL
-// detector, depth 4, and a fifth field in which a report lingers one step (automaton.c kmpb_filter6_build) -- so that
-// the row loop updates the state once per TWO bytes: S = ((S << 12) | 0xfff) & G[b0] & L[b1], G = (L << 6) | 0x3f in
-// the second half of the LUT's 256-byte rows.  After the update bits 24..29 are b0's reports, bits 18..23 b1's.
-#define F6_ARM 0x00020820u                                               // NUL stage pre-armed at depths 0..2
-#define LUT_G(word, sel) lds32(__byte_perm((word), lutlane + 128u, (sel)))
-#define SA_NEXT(word, sel) (S = (S * mul + 63u) & LUT_AT(word, sel))     // one byte (the resolve step's re-run)
-#define SA2_STEP(word, selA, selB, acc)                                        \
-    do {                                                                       \
-        S = (S * mul2 + 4095u) & LUT_G(word, selA) & LUT_AT(word, selB);       \
-        acc |= S;                                                              \
-    } while (0)
-#define SA2_WORD(word, acc)               \
-    do {                                  \
-        SA2_STEP(word, SEL0, SEL1, acc);  \
-        SA2_STEP(word, SEL2, SEL3, acc);  \
-    } while (0)
-#else
-#define SA_NEXT(word, sel) (S = (S * mul + 255u) & LUT_AT(word, sel))
-#endif
-#define SA_STEP(word, sel, acc) \
-    do {                        \
-        SA_NEXT(word, sel);     \
-        acc |= S;               \
-    } while (0)
-#define SA_WORD(word, acc)        \
-    do {                          \
-        SA_STEP(word, SEL0, acc); \
-        SA_STEP(word, SEL1, acc); \
-        SA_STEP(word, SEL2, acc); \
-        SA_STEP(word, SEL3, acc); \
-    } while (0)
-// same step, shifting "this byte is NUL" into zr (the first step ends up in the highest bit used) ...
-#ifdef KMPB_FILTER6
-#define SZ_STEP(word, sel)                   \
-    do {                                     \
-        SA_NEXT(word, sel);                  \
-        zr = __funnelshift_l(S << 8, zr, 1); \
-    } while (0)
-#define SV_STEP(word, sel)                                              \
-    do {                                                                \
-        SZ_STEP(word, sel);                                             \
-        cmr = __funnelshift_l((S & 0x007c0000u) + 0x7ffc0000u, cmr, 1); \
-    } while (0)
-#else
-#define SZ_STEP(word, sel)                 \
-    do {                                   \
-        SA_NEXT(word, sel);                \
-        zr = __funnelshift_l(S, zr, 1);    \
-    } while (0)
-// ... and "a candidate start fired" into cmr
-#define SV_STEP(word, sel)                                              \
-    do {                                                                \
-        SZ_STEP(word, sel);                                             \
-        cmr = __funnelshift_l((S & 0x7f000000u) + 0x7f000000u, cmr, 1); \
-    } while (0)
-#endif
-#define SV_WORD(word)        \
-    do {                     \
-        SV_STEP(word, SEL0); \
-        SV_STEP(word, SEL1); \
-        SV_STEP(word, SEL2); \
-        SV_STEP(word, SEL3); \
-    } while (0)
+// filter words of byte k (0..3) of `word`: the IDP.4A builds the whole shared address, byte * 128 + the lane's base
+// in table L (lutL) or G (lutG)
+#define LUT_L(word, k) lds32(__dp4a((uint32_t)(word), 0x80u << (8 * (k)), lutL))
+#define LUT_G(word, k) lds32(__dp4a((uint32_t)(word), 0x80u << (8 * (k)), lutG))
+// one two-byte update: bytes k0, k1 = k0 + 1 of `word`
+#define SA2(word, k0) (S = (S * mul2 + 4095u) & LUT_G(word, k0) & LUT_L(word, (k0) + 1))
+// one one-byte update (the resolve step's re-run)
+#define SA1(word, k) (S = (S * mul1 + 63u) & LUT_L(word, k))
 
-// what the slow path needs besides the event list
-struct slow_ctx {
-    const uint8_t *bytes; // absolute byte abs_base
-    uint64_t abs_base;
-    const uint64_t *offsets;
-    const uint32_t *vtab_g; // verification tables in global memory
-    uint32_t vtab_sa;       // ... or their shared address (vtab_in_smem)
-    uint32_t vtab_in_smem;
-    uint32_t one_off;       // word offset of the one-byte patterns' table, 0 = none
-    uint32_t scratch_sa;    // per-warp scratch: {ks, ke, b_abs, e_abs} of the items of either parity (2 x 32 B),
-                            // 32 words the resolve step publishes, item parity, the "previous item pending" flag, the NUL carry
-    uint32_t s_counts_sa;   // shared address of the shared counters, or 0
-    unsigned long long *g_counts;
+// The scratch words of a warp (128 bytes): two sets of 32 bytes, one per item parity --
+//   {ks, ke, b_rel, e_rel, row0 lo, row0 hi, carry, packets per byte}: the item's packets [ks, ke), its bytes
+//   [b_rel, e_rel) relative to row0 = the absolute position of its first row, 1 + the (relative) position of the last
+//   NUL byte among its events resolved so far (0: none), and (ke - ks) / (e_rel - b_rel) as a float --
+// then, at byte 64, {parity of the item being scanned, "the list holds events of the item before it"}.
+constexpr uint32_t SC_STATE = 64;
+
+// what a resolve step needs besides the events; every warp derives it from its own index (nothing of it has to live in
+// the row loop's registers)
+struct drain_args {
+    uint32_t q_sa;       // the warp's event ring
+    uint32_t scratch_sa; // the warp's scratch words
+    uint32_t lutL;       // the lane's base in table L
+    uint32_t vtab_sa;    // the probe tables in shared memory (vtab_in_smem)
+    uint32_t counts_sa;  // the shared counters, or 0
 };
-
-// the hot fields of slow_ctx, read once per resolve step (the context itself lives in local memory)
-struct verify_ctx {
-    uint32_t vtab_sa, one_off, s_counts_sa;
-};
-
-__device__ __forceinline__ void count_hit(const slow_ctx &c, const verify_ctx &v, uint32_t u)
+extern __shared__ __align__(1024) uint8_t smem[];
+__device__ __forceinline__ uint32_t warp_q_sa() { return saddr_of(smem + UN_OFF_Q) + (threadIdx.x >> 5) * (UN_QCAP * UN_Q_BYTES1); }
+__device__ __forceinline__ uint32_t warp_scratch_sa() { return saddr_of(smem + UN_OFF_SCRATCH) + (threadIdx.x >> 5) * 128; }
+__device__ __forceinline__ drain_args make_drain_args(const union_params &p)
 {
-    if (v.s_counts_sa) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(v.s_counts_sa + 4u * u) : "memory");
-    else atomicAdd(c.g_counts + u, 1ull);
+    drain_args d;
+    d.q_sa = warp_q_sa();
+    d.scratch_sa = warp_scratch_sa();
+    d.lutL = saddr_of(smem) + ((threadIdx.x & 31) << 2);
+    const uint32_t counts_bytes = p.counts_in_smem ? ((4u * p.n_uniq + 15u) & ~15u) : 0u;
+    d.vtab_sa = saddr_of(smem + UN_OFF_COUNTS) + counts_bytes;
+    d.counts_sa = p.counts_in_smem ? saddr_of(smem + UN_OFF_COUNTS) : 0u;
+    return d;
+}
+
+__device__ __forceinline__ void count_hit(const union_params &p, const drain_args &d, uint32_t u)
+{
+    if (d.counts_sa) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(d.counts_sa + 4u * u) : "memory");
+    else atomicAdd(p.uniq_counts + u, 1ull);
 }
 
 // 4 text bytes starting at byte `pos` of the event at entry_sa, of which the first `need` (>= 1) matter: from
-// the event while its 40 bytes last, then from global memory (never past the word that holds the last
-// needed byte, which lies inside the packet)
-__device__ __forceinline__ uint32_t text_window(const slow_ctx &c, uint32_t entry_sa, uint32_t pos, uint32_t need)
+// the event while its 36 bytes last, then from global memory (never past the word that holds the last
+// needed byte, which lies inside the packet).  Where the event's group lies in global memory follows from its
+// group index and its item's row0 in the warp's scratch words.
+__device__ __forceinline__ uint32_t text_window(const union_params &p, const drain_args &d, uint32_t entry_sa, uint32_t pos, uint32_t need)
 {
-    if (pos + 4 <= 40) return entry_window(entry_sa, pos);
-    const uint8_t *gw = c.bytes + (uint64_t)UN_GRP * (lds32v(entry_sa + 40) & 0x7fffffffu) + (pos & ~3u);
+    if (pos + 4 <= 36) {
+        const uint32_t a = entry_sa + (pos & ~3u);
+        return __funnelshift_r(lds32v(a), lds32v(a + 4), 8u * (pos & 3u));
+    }
+    const uint32_t meta = lds32v(entry_sa + 40);
+    const uint2 r0 = lds64v(d.scratch_sa + ((meta >> 31) << 5) + 16);
+    const uint8_t *gw = p.bytes + ((((uint64_t)r0.y << 32) | r0.x) - p.abs_base) + ((meta & 0x7fffffffu) << 5) + (pos & ~3u);
     const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(gw));
     const uint32_t hi = (pos & 3u) + (need < 4 ? need : 4u) > 4u ? __ldg(reinterpret_cast<const uint32_t *>(gw) + 1) : 0u;
     return __funnelshift_r(lo, hi, 8u * (pos & 3u));
 }
 
-// Every pattern that starts at byte `i` of the event at entry_sa and is at most `room` (>= 1) bytes long
-// is counted.  The candidate's first two bytes select one slot of the verification tables (automaton.c
-// build_verify_tables); the slot's records -- the patterns whose first two bytes hash there, usually those of one
-// two-byte prefix -- carry the pattern's first 8 bytes and their masks, so a record costs one 16-byte load and one
-// masked compare, and only a record that agrees on those bytes is looked at further.
+// Every pattern that starts at byte `i` (0..31) of the event at entry_sa and is at most `room` (>= 1) bytes long
+// is counted.  The candidate's first two bytes select one slot of probe table A (the two-byte patterns), its first
+// three one slot of table B (the longer ones); the slots' records carry the pattern's first 8 bytes and their masks,
+// so a record costs one 16-byte load and one masked compare, and only a record that agrees on those bytes is looked
+// at further.
 template <bool VS>
-__device__ __forceinline__ void verify_start(const slow_ctx &c, const verify_ctx &v, const uint4 hdr, uint32_t entry_sa, uint32_t i,
-                                             uint32_t room)
+__device__ __forceinline__ void verify_start(const union_params &p, const drain_args &d, uint32_t entry_sa, uint32_t i, uint32_t room)
 {
-    auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(v.vtab_sa + 4u * word) : __ldg(c.vtab_g + word); };
+    auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(d.vtab_sa + 4u * word) : __ldg(p.vtab + word); };
     auto vt4 = [&](uint32_t word) -> uint4 {
-        return VS ? lds128v(v.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint4 *>(c.vtab_g + word));
+        return VS ? lds128(d.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint4 *>(p.vtab + word));
     };
     auto vt2 = [&](uint32_t word) -> uint2 {
-        return VS ? lds64(v.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(c.vtab_g + word));
+        return VS ? lds64(d.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(p.vtab + word));
     };
-    // hdr = vtab[1..4]: slots, hash shift, records, pattern words
-    const uint32_t x0 = entry_window(entry_sa, i);
-    if (v.one_off) { // one-byte patterns: a direct table (room >= 1 always holds)
-        const uint32_t u = vt(v.one_off + (x0 & 0xffu));
-        if (u != 0xffffffffu) count_hit(c, v, u);
+    // text bytes i..i+3 (i + 4 <= 36) and, if a pattern that long fits at all, i+4..i+7
+    const uint32_t x0 = text_window(p, d, entry_sa, i, 4);
+    if (p.vt_one) { // one-byte patterns: a direct table (room >= 1 always holds)
+        const uint32_t u = vt(p.vt_one + (x0 & 0xffu));
+        if (u != 0xffffffffu) count_hit(p, d, u);
     }
-    const uint2 e = vt2(hdr.x + 2u * (((x0 & 0xffffu) * 0x9e3779b1u) >> hdr.y)); // {first record, records}
-    if (e.y == 0 || room < 2) return;
-    const uint32_t x1 = room > 4 ? text_window(c, entry_sa, i + 4, room - 4) : 0u; // text bytes i+4..i+7
-    for (uint32_t r = hdr.z + 8u * e.x, rend = r + 8u * e.y; r != rend; r += 8) {
+    if (room < 2) return;
+    uint2 ea = make_uint2(0, 0), eb = make_uint2(0, 0); // {first record, records}
+    if (p.vt_slots_a) ea = vt2(p.vt_slots_a + 2u * (((x0 & 0xffffu) * 0x9e3779b1u) >> p.vt_shift_a));
+    if (p.vt_slots_b && room >= 3) eb = vt2(p.vt_slots_b + 2u * (((x0 & 0xffffffu) * 0x9e3779b1u) >> p.vt_shift_b));
+    const uint32_t nrec = ea.y + eb.y;
+    if (nrec == 0) return; // most candidates end here: no pattern begins with these bytes
+    const uint32_t x1 = room > 4 ? text_window(p, d, entry_sa, i + 4, room - 4) : 0u;
+    for (uint32_t j = 0; j < nrec; j++) {
+        const uint32_t r = p.vt_rec + 8u * (j < ea.y ? ea.x + j : eb.x + (j - ea.y));
         const uint4 a = vt4(r); // pattern bytes 0..3, their mask, bytes 4..7, their mask
         if ((((x0 ^ a.x) & a.y) | ((x1 ^ a.z) & a.w)) != 0) continue;
         const uint2 b = vt2(r + 4); // length, distinct id
@@ -399,154 +374,127 @@ __device__ __forceinline__ void verify_start(const slow_ctx &c, const verify_ctx
         if (m > room) continue;
         bool same = true;
         if (m > 8) {
-            const uint32_t pw0 = hdr.w + vt(r + 6);
-            for (uint32_t j = 8; j < m && same; j += 4) { // pattern bytes j..j+3 against text bytes i+j..
-                const uint32_t pw = vt(pw0 + (j >> 2)), rem = m - j;
-                const uint32_t diff = text_window(c, entry_sa, i + j, rem) ^ pw;
+            const uint32_t pw0 = p.vt_blob + vt(r + 6);
+            for (uint32_t jj = 8; jj < m && same; jj += 4) { // pattern bytes jj..jj+3 against text bytes i+jj..
+                const uint32_t pw = vt(pw0 + (jj >> 2)), rem = m - jj;
+                const uint32_t diff = text_window(p, d, entry_sa, i + jj, rem) ^ pw;
                 same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
             }
         }
-        if (same) count_hit(c, v, b.y);
+        if (same) count_hit(p, d, b.y);
     }
 }
 
-// Resolve the warp's n pending events (n <= 32).  The warp's carry -- 1 + absolute position of the last NUL byte
-// seen in the events it has resolved so far (0 = none) -- lives in its scratch words (bytes 200..207), not in a
-// register of the row loop.
+// Resolve the n (<= 32) oldest events of the warp's ring, which start at slot `head`.
 //
-// Phase 1, one event per lane: which start positions fired, where the NULs are, which packet(s) the
-// group lies in -> mask of candidate starts that are alive (inside the item, no NUL before them in their
+// Phase 1, one event per lane: which start positions of the event's quarter(s) fired, where the NULs are, which
+// packet(s) they lie in -> mask of candidate starts that are alive (inside the item, no NUL before them in their
 // packet) and mask of packet boundaries inside the group.
-// Phase 2, one alive candidate per lane, whichever event it came from: hash lookup and count.
+// Phase 2, every lane its own alive candidates: probe, compare, count.
 //
-//
-// The pending events belong to the work item the warp is scanning or to the one before it (the row loop sees to
-// that); an event carries its item's parity, and the packets [ks, ke) and bytes [b_abs, e_abs) of both items wait in
-// the warp's scratch words, where the warp put them when it took the item: no lane has to look them up in global
-// memory, and the row loop does not keep them in registers.
-__device__ __noinline__ void drain_events(const slow_ctx &c, const uint32_t q_sa, const uint32_t n, const uint32_t lutlane,
-                                          const uint32_t mul)
+// The events belong to the work item the warp is scanning or to the one before it (the row loop sees to that); an
+// event carries its item's parity, and what the resolve step has to know about either item waits in the warp's
+// scratch words, where the warp put it when it took the item: no lane has to look anything up in global memory for
+// it, and the row loop does not keep it in registers.  Positions are relative to the item's row0 (32 bits).
+__device__ __noinline__ void drain_events(const union_params &p, const uint32_t head, const uint32_t n)
 {
+    const drain_args d = make_drain_args(p);
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lutL = d.lutL, mul1 = p.mul64;
+    uint32_t lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     __syncwarp();
-    const uint32_t entry_sa = q_sa + lane * (UN_Q_WORDS * 4);
-    uint32_t cm = 0, zm = 0;
-    uint64_t gq = 0, b_abs = 0, e_abs = 0; // my group's first byte; my item's byte range (absolute)
-    uint32_t ks = 0, ke = 0;
+    const uint32_t entry_sa = d.q_sa + ((head + lane) & (UN_QCAP - 1)) * UN_Q_BYTES1;
+    uint32_t cm = 0, zm = 0, gq = 0, par = 0;
+    uint32_t ks = 0, ke = 0, b_rel = 0, e_rel = 0, row0_lo = 0, row0_hi = 0, carry = 0;
+    float per_byte = 0.f;
     if (lane < n) {
-        const uint2 t = lds64v(entry_sa + 40); // group index | item parity << 31, quarter reports
-        gq = c.abs_base + (uint64_t)UN_GRP * (t.x & 0x7fffffffu);
-        const uint32_t set_sa = c.scratch_sa + ((t.x >> 31) << 5); // my item's {ks, ke, b_abs, e_abs}
-        const uint4 iw = lds128v(set_sa);
-        const uint2 iw2 = lds64v(set_sa + 16);
-        ks = iw.x;
-        ke = iw.y;
-        b_abs = (uint64_t)iw.w << 32 | iw.z;
-        e_abs = (uint64_t)iw2.y << 32 | iw2.x;
-        // Re-run the filter over the quarters that reported, this time recording which start positions
-        // fired and which bytes are NUL.  Quarter k: bytes 8k..8k+10 (three bytes of run-in, then starts
-        // 8k..8k+7 report at bytes 8k+3..8k+10); the NUL bit is exact from the first byte on.
-#ifdef KMPB_UN_LEAN_EVENTS
-        // Experimental (not the default, not yet run on a GPU): the row loop pushed only the
-        // group index and the reports; the group's 32 bytes and the 8 after them come from L2 now (the row was read
-        // a few microseconds ago) and go into the event slot, where the rest of the resolve step expects them.
-        // Readable: the batch up to its end rounded up to 32 (include/kmpb200.h); a group at or past the item's end
-        // reported from stale ring bytes and holds nothing of this item.
-        uint32_t reports = t.y;
-        {
-            uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;
-            uint2 g2 = make_uint2(0, 0);
-            if (gq < e_abs) {
-                const uint8_t *src = c.bytes + (uint64_t)UN_GRP * (t.x & 0x7fffffffu);
-                g0 = __ldg(reinterpret_cast<const uint4 *>(src));
-                g1 = __ldg(reinterpret_cast<const uint4 *>(src + 16));
-                if (gq + UN_GRP < e_abs) g2 = __ldg(reinterpret_cast<const uint2 *>(src + 32));
-            } else {
-                reports = 0;
-            }
-            sts128v(entry_sa, g0.x, g0.y, g0.z, g0.w);
-            sts128v(entry_sa + 16, g1.x, g1.y, g1.z, g1.w);
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(entry_sa + 32), "r"(g2.x), "r"(g2.y) : "memory");
-        }
-#else
-        const uint32_t reports = t.y;
-#endif
-        uint32_t quarters = ((((reports & 0x7f7f7f7fu) + 0x7f7f7f7fu) | reports) & 0x80808080u); // bit 8k+7: quarter k
+        const uint2 t = lds64v(entry_sa + 40); // group index (relative to row0) | item parity << 31, quarter reports
+        par = t.x >> 31;
+        gq = (t.x & 0x7fffffffu) << 5;
+        const uint32_t set_sa = d.scratch_sa + (par << 5); // my item's scratch set
+        const uint4 s0 = lds128v(set_sa), s1 = lds128v(set_sa + 16);
+        ks = s0.x; ke = s0.y; b_rel = s0.z; e_rel = s0.w;
+        row0_lo = s1.x; row0_hi = s1.y; carry = s1.z; per_byte = __uint_as_float(s1.w);
+        // Re-run the filter over the quarters that reported (usually one), one byte per update, this time recording
+        // which start positions fired and which bytes are NUL.  Quarter k: bytes 8k..8k+11 -- three bytes of run-in,
+        // then the starts 8k..8k+8 report at the bytes 8k+3..8k+11, and so do the NULs among the bytes 8k..8k+8 (the
+        // quarters of the row loop overlap by one start; OR-ing a bit twice changes nothing).
+        uint32_t quarters = (((t.y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t.y) & 0x80808080u; // bit 8k+7: quarter k
         while (quarters) {
             const uint32_t k8 = (__ffs(quarters) - 1) & ~7u; // 8k
             quarters &= quarters - 1;
             const uint32_t w0 = lds32v(entry_sa + k8), w1 = lds32v(entry_sa + k8 + 4), w2 = lds32v(entry_sa + k8 + 8);
-#ifdef KMPB_FILTER6
-            // quarter k here: bytes 8k..8k+11, starts 8k..8k+8 (the quarters of the row loop overlap by one start;
-            // OR-ing a start bit twice changes nothing)
-            uint32_t S = F6_ARM, cmr = 0, zr = 0;
-            SZ_STEP(w0, SEL0); SZ_STEP(w0, SEL1); SZ_STEP(w0, SEL2);
-            SV_STEP(w0, SEL3);
-            SV_WORD(w1);
-            SV_WORD(w2);
-            cm |= (__brev(cmr) >> 23) << k8;
-            zm |= (__brev(zr) >> 20) << k8;
-#else
-            uint32_t S, cmr = 0, zr;
-            S = LUT_AT(w0, SEL0) & 0x808080ffu;
-            zr = S >> 31;
-            SZ_STEP(w0, SEL1); SZ_STEP(w0, SEL2);
-            SV_STEP(w0, SEL3);
-            SV_WORD(w1);
-            SV_STEP(w2, SEL0); SV_STEP(w2, SEL1); SV_STEP(w2, SEL2);
-            cm |= (__brev(cmr) >> 24) << k8;
-            zm |= (__brev(zr) >> 21) << k8;
-#endif
+            uint32_t S = 0, cmr = 0, zr = 0;
+#define SV1(word, k)                                                    \
+    do {                                                                \
+        SA1(word, k);                                                   \
+        zr = __funnelshift_l(S << 8, zr, 1);                            \
+        cmr = __funnelshift_l((S & 0x007c0000u) + 0x7ffc0000u, cmr, 1); \
+    } while (0)
+            SA1(w0, 0); SA1(w0, 1); SA1(w0, 2);
+            SV1(w0, 3);
+            SV1(w1, 0); SV1(w1, 1); SV1(w1, 2); SV1(w1, 3);
+            SV1(w2, 0); SV1(w2, 1); SV1(w2, 2); SV1(w2, 3);
+#undef SV1
+            cm |= (__brev(cmr) >> 23) << k8; // the first report is the highest of the 9 bits
+            zm |= (__brev(zr) >> 23) << k8;
         }
-        // the item's first and last rows overhang it: starts count inside [b_abs, e_abs) only, and bytes
-        // past e_abs may be stale ring contents, so NULs count below e_abs only
-        const uint32_t lo = b_abs > gq ? (uint32_t)min(b_abs - gq, (uint64_t)32) : 0u;
-        const uint32_t hi = e_abs > gq ? (uint32_t)min(e_abs - gq, (uint64_t)32) : 0u;
+        // the item's first and last rows overhang it: starts count inside [b_rel, e_rel) only, and bytes
+        // past e_rel may be anything, so NULs count below e_rel only
+        const uint32_t lo = clamp32((int32_t)b_rel - (int32_t)gq), hi = clamp32((int32_t)e_rel - (int32_t)gq);
         cm &= bit_window(lo, hi);
         zm &= bit_window(0, hi);
     }
-    // last NUL before my group: the nearest earlier event that holds one, else the warp's carry
-    const uint64_t mylast1 = zm ? gq + (32u - __clz(zm)) : 0ull; // 1 + position of my last NUL
-    const uint32_t nulm = __ballot_sync(FULL, zm != 0);
-    const uint32_t below = nulm & ((1u << lane) - 1u);
-    const uint64_t from_below = __shfl_sync(FULL, mylast1, below ? 31 - __clz(below) : 0);
-    const uint2 cw = lds64v(c.scratch_sa + 200);
-    const uint64_t carry = (uint64_t)cw.y << 32 | cw.x;
-    const uint64_t prev1 = below ? from_below : carry;
-    const uint64_t from_top = __shfl_sync(FULL, mylast1, nulm ? 31 - __clz(nulm) : 0);
+    // last NUL before my event's bytes: the nearest earlier event of the same item that holds one, else the carry of
+    // my item (the events of an item are in stream order; those of the older item come first)
+    const uint32_t mylast1 = zm ? gq + (32u - __clz(zm)) : 0u; // 1 + position of my last NUL
+    const uint32_t nulm = __ballot_sync(FULL, zm != 0), parm = __ballot_sync(FULL, par != 0);
+    const uint32_t mine = nulm & (par ? parm : ~parm);
+    const uint32_t below = mine & lt;
+    const uint32_t from_below = __shfl_sync(FULL, mylast1, below ? 31 - __clz(below) : 0);
+    const uint32_t prev1 = below ? from_below : carry;
+    // the carries: the last NUL of either item among these events
+    const uint32_t top0 = nulm & ~parm, top1 = nulm & parm;
+    const uint32_t new0 = __shfl_sync(FULL, mylast1, top0 ? 31 - __clz(top0) : 0);
+    const uint32_t new1 = __shfl_sync(FULL, mylast1, top1 ? 31 - __clz(top1) : 0);
     __syncwarp();
-    if (nulm && lane == 0)
-        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(c.scratch_sa + 200), "r"((uint32_t)from_top), "r"((uint32_t)(from_top >> 32)) : "memory");
+    if (lane == 0) {
+        if (top0) sts32v(d.scratch_sa + 24, new0);
+        if (top1) sts32v(d.scratch_sa + 32 + 24, new1);
+    }
 
     uint32_t am = 0, bm = 0, nextb = 255; // alive candidates; packet starts inside the group (bit = offset);
                                           // offset of the first packet start at or after the group's end
     if (cm) {
         // The packet that holds my first candidate: the last k in [ks, ke) with offsets[k] <= p0.  First
         // guess by interpolation (exact for equal-sized packets), then a binary search in what is left.
-        const uint64_t p0 = gq + (__ffs(cm) - 1);
+        // Offsets relative to row0 fit 32 bits and need the low words only.
+        const uint32_t *olo = reinterpret_cast<const uint32_t *>(p.offsets);
+        auto orel = [&](uint32_t k) -> uint32_t { return __ldg(olo + 2u * k) - row0_lo; };
+        const uint32_t p0 = gq + (__ffs(cm) - 1);
         uint32_t k = ks, k1 = ke;
         {
-            const float frac = (float)(uint32_t)(p0 - b_abs) / (float)(uint32_t)(e_abs - b_abs);
-            uint32_t kg = ks + (uint32_t)(frac * (float)(ke - ks));
+            uint32_t kg = ks + (uint32_t)((float)(p0 - b_rel) * per_byte);
             kg = kg >= ke ? ke - 1 : kg;
-            const uint64_t o0 = __ldg(c.offsets + kg), o1 = __ldg(c.offsets + kg + 1);
+            const uint32_t o0 = orel(kg), o1 = orel(kg + 1);
             if (o0 <= p0) {
                 k = kg;
                 if (p0 < o1) k1 = kg + 1;
-                else k = kg + 1; // offsets[kg + 1] <= p0 < e_abs, so kg + 1 < ke
+                else k = kg + 1; // offsets[kg + 1] <= p0 < e_rel, so kg + 1 < ke
             } else {
                 k1 = kg;
             }
         }
         while (k1 - k > 1) {
             const uint32_t mid = k + (k1 - k) / 2;
-            if (__ldg(c.offsets + mid) <= p0) k = mid; else k1 = mid;
+            if (orel(mid) <= p0) k = mid; else k1 = mid;
         }
-        uint64_t ps = __ldg(c.offsets + k), pe = __ldg(c.offsets + k + 1);
-        bool dead = prev1 > ps; // a NUL in [ps, group): kmp_matcher's strlen() stopped before my group
-        uint32_t a = ps > gq ? (uint32_t)(ps - gq) : 0u; // the packet [ps, pe) covers my group from offset a on
+        uint32_t ps = orel(k), pe = orel(k + 1);
+        bool dead = prev1 > ps; // a NUL in [ps, my bytes): kmp_matcher's strlen() stopped before them
+        uint32_t a = ps > gq ? ps - gq : 0u; // the packet [ps, pe) covers my group from offset a on
         for (;;) {
-            const uint32_t b = pe - gq >= 32 ? 32u : (uint32_t)(pe - gq);
+            const uint32_t b = pe - gq >= 32 ? 32u : pe - gq;
             const uint32_t seg = bit_window(a, b), z = zm & seg;
             if (!dead) am |= cm & seg & (z ? (z & (0u - z)) - 1u : FULL); // starts before the packet's first NUL
             if (b == 32) break;
@@ -556,42 +504,35 @@ __device__ __noinline__ void drain_events(const slow_ctx &c, const uint32_t q_sa
             dead = false;
             k++;
             ps = pe;
-            pe = __ldg(c.offsets + k + 1);
+            pe = orel(k + 1);
         }
-        nextb = pe - gq > 255 ? 255u : (uint32_t)(pe - gq);
+        nextb = pe - gq > 255 ? 255u : pe - gq;
     }
     // publish what phase 2 needs next to the event's bytes
     if (lane < n) {
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(entry_sa + 44), "r"(bm) : "memory"); // over the quarter reports
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.scratch_sa + 64 + 4 * lane), "r"(nextb) : "memory");
+        sts32v(entry_sa + 36, nextb);
+        sts32v(entry_sa + 44, bm); // over the quarter reports
     }
     // alive candidates, numbered across the lanes
     const uint32_t cnt = __popc(am);
     uint32_t incl = cnt;
 #pragma unroll
-    for (uint32_t d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += v;
+    for (uint32_t dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, dd);
+        if (lane >= dd) incl += v;
     }
     const uint32_t total = __shfl_sync(FULL, incl, 31);
     const uint32_t excl = incl - cnt;
     __syncwarp();
-    verify_ctx vc;
-    vc.vtab_sa = c.vtab_sa;
-    vc.one_off = c.one_off;
-    vc.s_counts_sa = c.s_counts_sa;
-    // vtab[1..4]: where the slots, the records and the pattern words are
-    const uint4 vhdr = total == 0 ? make_uint4(0, 0, 0, 0)
-                       : c.vtab_in_smem ? make_uint4(lds32(c.vtab_sa + 4), lds32(c.vtab_sa + 8), lds32(c.vtab_sa + 12), lds32(c.vtab_sa + 16))
-                                        : make_uint4(__ldg(c.vtab_g + 1), __ldg(c.vtab_g + 2), __ldg(c.vtab_g + 3), __ldg(c.vtab_g + 4));
+    // one alive candidate per lane, whichever event it belongs to
     for (uint32_t t0 = 0; t0 < total; t0 += 32) {
         const uint32_t t = t0 + lane;
         // owner of candidate t: the first lane whose inclusive count exceeds t
         uint32_t l = 0;
 #pragma unroll
-        for (uint32_t s = 16; s; s >>= 1) {
-            const uint32_t v = __shfl_sync(FULL, incl, l + s - 1);
-            if (v <= t) l += s;
+        for (uint32_t st = 16; st; st >>= 1) {
+            const uint32_t v = __shfl_sync(FULL, incl, l + st - 1);
+            if (v <= t) l += st;
         }
         l &= 31;
         uint32_t m = __shfl_sync(FULL, am, l);
@@ -599,25 +540,25 @@ __device__ __noinline__ void drain_events(const slow_ctx &c, const uint32_t q_sa
         if (t < total) {
             for (uint32_t j = first; j < t; j++) m &= m - 1;
             const uint32_t i = __ffs(m) - 1;
-            const uint32_t owner_sa = q_sa + l * (UN_Q_WORDS * 4);
-            const uint32_t obm = lds32v(owner_sa + 44), onext = lds32v(c.scratch_sa + 64 + 4 * l);
+            const uint32_t owner_sa = d.q_sa + ((head + l) & (UN_QCAP - 1)) * UN_Q_BYTES1;
+            const uint32_t onext = lds32v(owner_sa + 36), obm = lds32v(owner_sa + 44);
             const uint32_t above = obm & ~((2u << i) - 1u); // packet starts after byte i
             const uint32_t room = (above ? (uint32_t)__ffs(above) - 1u : onext) - i;
-            if (c.vtab_in_smem) verify_start<true>(c, vc, vhdr, owner_sa, i, room);
-            else verify_start<false>(c, vc, vhdr, owner_sa, i, room);
+            if (p.vtab_in_smem) verify_start<true>(p, d, owner_sa, i, room);
+            else verify_start<false>(p, d, owner_sa, i, room);
         }
     }
     __syncwarp();
 }
 
-// NUL-dense row (many groups reported and the list is full).  An event without candidates exists only to tell later
-// candidates where the last NUL before them is; when the next event of the row is of the same kind, that one tells
-// them a later NUL and this one is not needed: its reports are cleared (binary payloads: one event per row instead
-// of one per group).  m = lanes with reports.  Kept out of line: the row loop should stay small.
-__device__ __noinline__ uint32_t drop_superseded(uint32_t tops, const uint32_t m)
+// NUL-dense row.  An event without candidates exists only to tell later candidates where the last NUL before them
+// is; when the next event of the row is of the same kind, that one tells them a later NUL and this one is not needed:
+// its reports are cleared (binary payloads: one event per row instead of one per group).  m = lanes with reports,
+// has_cand = my reports hold a candidate.  Kept out of line: the row loop should stay small.
+__device__ __noinline__ uint32_t drop_superseded(uint32_t tops, const uint32_t m, const bool has_cand)
 {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t mc = __ballot_sync(FULL, (tops & 0x7f7f7f7fu) != 0); // lanes with candidates
+    const uint32_t mc = __ballot_sync(FULL, has_cand);                  // lanes with candidates
     const uint32_t above = m & ~((2u << lane) - 1u);                    // reporting lanes above me
     if (!((mc >> lane) & 1u) && above && !((mc >> (__ffs(above) - 1)) & 1u)) tops = 0;
     return tops;
@@ -628,90 +569,36 @@ __device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(FULL, v
 __device__ __forceinline__ uint64_t uni(uint64_t v) { return __shfl_sync(FULL, v, 0); }
 __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_constant__ union_params p)
 {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    // the LUT sits at the first 64 KB-aligned shared address inside the dynamic allocation
-    const uint32_t dyn_saddr = saddr_of(smem);
-    uint32_t dyn_size;
-    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
-    const uint32_t lut_off = (0x10000u - (dyn_saddr & 0xffffu)) & 0xffffu;
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);                      // L, then G
+    uint32_t *s_misc = reinterpret_cast<uint32_t *>(smem + UN_OFF_MISC);
+    uint32_t *s_counts = reinterpret_cast<uint32_t *>(smem + UN_OFF_COUNTS);
     const uint32_t counts_bytes = p.counts_in_smem ? ((4u * p.n_uniq + 15u) & ~15u) : 0u;
-    const uint32_t vtab_bytes = p.vtab_in_smem ? 4u * p.vtab_words : 0u;
-    const uint32_t front_bytes = UN_FRONT_FIXED + counts_bytes;
-    if (lut_off < front_bytes || lut_off + UN_LUT_BYTES + UN_RING_BYTES + vtab_bytes > dyn_size) {
-        // unexpected shared-memory window base: refuse rather than compute something wrong
-        if (threadIdx.x == 0) atomicOr(&p.work[1], 2u);
-        return;
-    }
-    uint8_t *lut = smem + lut_off;
-    uint8_t *ring_all = lut + UN_LUT_BYTES;
-    uint8_t *q_all = smem;
-    uint8_t *scratch_all = smem + UN_Q_BYTES;
-    uint32_t *s_lut_saddr = reinterpret_cast<uint32_t *>(scratch_all + UN_SCRATCH_BYTES);
-    uint32_t *s_counts = reinterpret_cast<uint32_t *>(s_lut_saddr + 4);
-    uint32_t *s_vtab = reinterpret_cast<uint32_t *>(ring_all + UN_RING_BYTES); // behind the rings
+    uint32_t *s_vtab = reinterpret_cast<uint32_t *>(smem + UN_OFF_COUNTS + counts_bytes);
 
-    for (uint32_t i = threadIdx.x; i < 256 * 32; i += UN_THREADS)
-#ifdef KMPB_FILTER6
-    {
+    for (uint32_t i = threadIdx.x; i < 256 * 32; i += UN_THREADS) {
         const uint32_t f = p.filter[i >> 5];
-        reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + (i & 31)] = f;
-        reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + 32 + (i & 31)] = (f << 6) | 0x3fu;
+        lut[i] = f;                                // L[c] for lane i & 31
+        lut[256 * 32 + i] = (f << 6) | 0x3fu;      // G[c]
     }
-#else
-        reinterpret_cast<uint32_t *>(lut)[(i >> 5) * 64 + (i & 31)] = p.filter[i >> 5];
-#endif
     if (p.counts_in_smem)
         for (uint32_t i = threadIdx.x; i < p.n_uniq; i += UN_THREADS) s_counts[i] = 0;
     if (p.vtab_in_smem)
         for (uint32_t i = threadIdx.x; i < p.vtab_words; i += UN_THREADS) s_vtab[i] = p.vtab[i];
-    if (threadIdx.x == 0) *s_lut_saddr = dyn_saddr + lut_off;
-    if (threadIdx.x < UN_WARPS) { // per-warp item parity and "previous item pending" flag
-        reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[48] = 0;
-        reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[49] = 0;
-        reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[50] = 0; // the warp's NUL carry
-        reinterpret_cast<uint32_t *>(scratch_all + threadIdx.x * 256)[51] = 0;
-    }
+    for (uint32_t i = threadIdx.x; i < UN_SCRATCH_BYTES / 4; i += UN_THREADS)
+        reinterpret_cast<uint32_t *>(smem + UN_OFF_SCRATCH)[i] = 0; // item parity, pending flag, carries
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = uni(threadIdx.x >> 5);
-    // per-warp row ring: UN_SLOTS slots of one row (+16 bytes) each
-    // Inside a slot lane l owns bytes [32 l, 32 l + 32); lanes 4..7, 12..15, ... keep their two 16-byte
-    // halves swapped, which makes the 16-byte copies and reads of a quarter-warp hit 8 different bank groups.
-    const uint32_t ring_sa = saddr_of(ring_all) + warp * (UN_SLOTS * UN_SLOT_BYTES);
-    const uint32_t offtail = UN_ROW;
-#ifdef KMPB_UN_NOSWIZZLE
-    const uint32_t off0 = lane * UN_GRP, off1 = off0 + 16, offla = off0 + UN_GRP;
-#else
-    const uint32_t off0 = lane * UN_GRP + ((lane >> 2) & 1u) * 16, off1 = off0 ^ 16u;
-#ifdef KMPB_UN_COALESCED_COPY
-    const uint32_t coff = (lane * 16) ^ (((lane >> 3) & 1u) << 4); // slot offset of row bytes [16 lane, 16 lane + 16)
-#endif
-    // lane 31's lookahead: the slot's tail, or (three slots) the first bytes of the following slot
-    const uint32_t offla = lane == 31 ? UN_ROW : (lane + 1) * UN_GRP + (((lane + 1) >> 2) & 1u) * 16;
-#endif
     __syncthreads();
 
-    // read back through shared memory so that no LUT load can be scheduled above the barrier
-    const uint32_t lutlane = *s_lut_saddr + (lane << 2);
-    const uint32_t mul = p.mul256;
-#ifdef KMPB_FILTER6
+        const uint32_t lutL = saddr_of(lut) + (lane << 2), lutG = lutL + UN_LUT_BYTES;
     const uint32_t mul2 = p.mul4096;
-#endif
-    uint32_t lt;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
-    const uint32_t q_sa = saddr_of(q_all) + warp * (UN_QCAP * UN_Q_WORDS * 4);
-    slow_ctx sc;
-    sc.bytes = p.bytes;
-    sc.abs_base = p.abs_base;
-    sc.offsets = p.offsets;
-    sc.vtab_g = p.vtab;
-    sc.vtab_sa = saddr_of(s_vtab);
-    sc.vtab_in_smem = p.vtab_in_smem;
-    sc.one_off = p.vtab_one_off;
-    sc.scratch_sa = saddr_of(scratch_all) + warp * 256;
-    sc.s_counts_sa = p.counts_in_smem ? saddr_of(s_counts) : 0u;
-    sc.g_counts = p.uniq_counts;
+    uint32_t qn = 0, qw = 0; // pending events and the ring slot the next one goes to (the oldest sits at qw - qn)
 
-    uint32_t qn = 0;         // pending events
+    // resolve the oldest min(qn, 32) events
+    auto resolve_oldest = [&]() {
+        const uint32_t n = qn < UN_QDRAIN ? qn : UN_QDRAIN;
+        drain_events(p, (qw - qn) & (UN_QCAP - 1), n);
+        qn -= n;
+    };
 
     for (;;) {
         uint32_t item = 0;
@@ -722,227 +609,150 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         if (ks >= ke) continue;
         const uint64_t b_abs = uni(p.offsets[ks]), e_abs = uni(p.offsets[ke]);
         if (b_abs == e_abs) continue;
-        if (e_abs - b_abs >= (1ull << 31)) { // a packet over 2 GiB: outside the documented limits
+        if (e_abs - b_abs >= (1ull << 31) - 4096) { // a packet of about 2 GiB: outside the documented limits
             if (lane == 0) atomicOr(&p.work[1], 1u);
             continue;
         }
-        // What the slow path needs to know about this item goes into the scratch set of the item's parity.  The set
-        // still belongs to the item before the previous one; its events are gone unless the list has not been
-        // emptied since then (flag word 49: "the list holds events of the previous item"), in which case it is now.
-        const uint2 st = lds64v(sc.scratch_sa + 192); // parity of the previous item, pending flag
+        // What the resolve step needs to know about this item goes into the scratch set of the item's parity.  The
+        // set still belongs to the item before the previous one; its events are gone unless the list has not been
+        // resolved since then (the flag: "the list holds events of the item before the one being scanned"), in
+        // which case they are now.
+        const uint2 st = lds64v(warp_scratch_sa() + SC_STATE); // parity of the previous item, pending flag
         const uint32_t par = st.x ^ 1u;
-        if (qn && st.y) {
-            drain_events(sc, q_sa, qn, lutlane, mul);
-            qn = 0;
-        }
+        if (qn && st.y)
+            while (qn) resolve_oldest();
         __syncwarp();
-        if (lane == 0) {
-            const uint32_t set_sa = sc.scratch_sa + (par << 5);
-            sts128v(set_sa, ks, ke, (uint32_t)b_abs, (uint32_t)(b_abs >> 32));
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(set_sa + 16), "r"((uint32_t)e_abs), "r"((uint32_t)(e_abs >> 32)) : "memory");
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sc.scratch_sa + 192), "r"(par), "r"(qn ? 1u : 0u) : "memory");
-        }
         const uint64_t row0 = b_abs & ~127ull; // absolute position of the item's first row
-#ifdef KMPB_UN_COALESCED_COPY
-        const uint8_t *textl = p.bytes + (row0 - p.abs_base) + lane * 16; // the 16 bytes of the first row I copy first
-#else
+        const uint32_t b_rel = (uint32_t)(b_abs - row0), e_rel = (uint32_t)(e_abs - row0);
+        if (lane == 0) {
+            const uint32_t set_sa = warp_scratch_sa() + (par << 5);
+            sts128v(set_sa, ks, ke, b_rel, e_rel);
+            sts128v(set_sa + 16, (uint32_t)row0, (uint32_t)(row0 >> 32), 0u, __float_as_uint((float)(ke - ks) / (float)(e_rel - b_rel)));
+            sts64v(warp_scratch_sa() + SC_STATE, par, qn ? 1u : 0u);
+        }
         const uint8_t *textl = p.bytes + (row0 - p.abs_base) + lane * UN_GRP; // my 32 bytes of the item's first row
-#endif
-        const uint32_t e_rel = (uint32_t)(e_abs - row0);
-        const uint32_t load_end = (e_rel + 15u) & ~15u;
-        const uint32_t nrows = (e_rel + UN_ROW - 1) / UN_ROW;
-        // my group's index in row 0, in 32-byte units (< 2^31: a batch is below 64 GiB), and the item's parity
-        const uint32_t g32 = ((uint32_t)((row0 - p.abs_base) >> 5) + lane) | par << 31;
+        const uint32_t load_end = (e_rel + 31u) & ~31u; // readable: the batch up to its end rounded up to 32 (kmpb200.h)
+        // my group of the row at item offset `off` is loaded when off < lim; lane 31's lookahead when off + 32 < lim
+        const uint32_t lim = load_end > lane * UN_GRP ? load_end - lane * UN_GRP : 0u;
+        // my group's index in row 0 (relative to row0, in 32-byte units) and the item's parity
+        const uint32_t g32 = lane | par << 31;
 
-        // Every lane copies its own 32 bytes (lane 31 also the 16 bytes after the row -- they follow its own
-        // -- into the slot's tail) with 16-byte asynchronous copies.  One commit group per call, also when there is nothing left to copy, so
-        // that "all but the newest UN_SLOTS-1 groups are complete" always means "the row about to be
-        // scanned has arrived".  (A chunk-major slot layout, free of bank conflicts on both sides, measured
-        // 14 % slower on the fast path alone.)
-#ifdef KMPB_UN_COALESCED_COPY
-        // Which lane copies which 16 bytes is free (the slot is read after a warp barrier): each copy instruction
-        // moves 512 CONTIGUOUS bytes -- lane l the bytes [16 l, 16 l + 16) of the row's first and of its second half --
-        // instead of every other 16-byte piece.  The per-instruction counters of the capture in profiles/ show why: the
-        // strided form costs 14 shared-memory wavefronts per copy instruction instead of 4 (the data arrives by
-        // 32-byte sectors of which half is used) and fetches every sector of the row twice from L2.  The byte at row
-        // offset x still lands at slot offset x ^ (((x >> 7) & 1) << 4), so nothing else changes.
-        auto issue_row = [&](uint32_t r, uint32_t slot) {
-            const uint32_t row = r * UN_ROW;
-            const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES;
-            const uint8_t *src = add_wide(textl, row); // textl: 16 bytes per lane in this form
-            if (row + UN_SLOT_BYTES <= load_end) {
-                cp_async16(dst + coff, src);
-                cp_async16(dst + coff + 512, src + 512);
-                if (UN_TAIL) cp_async16_if(lane == 31, dst + offtail, src + (UN_ROW - 16 * 31));
-            } else if (row < e_rel) { // r < nrows
-                const uint32_t x = row + lane * 16;
-                if (x < load_end) cp_async16(dst + coff, src);
-                if (x + 512 < load_end) cp_async16(dst + coff + 512, src + 512);
-                if (UN_TAIL && lane == 31 && row + UN_ROW < load_end) cp_async16(dst + offtail, src + (UN_ROW - 16 * 31));
-            }
-            cp_async_commit();
+        // The row at item offset `off`, global -> registers: every lane its own 32 bytes with one 256-bit load, lane 31
+        // also the 4 bytes after the row (its lookahead; the other lanes find theirs in the next lane's registers).
+        // Rows past the item's end and the lanes past load_end in its last row load nothing and keep what they held:
+        // whatever they report from it is cut to the item's byte range by the resolve step.  The L2 prefetch of the
+        // row UN_PF rows further on rides on the same address.
+        auto load_row = [&](const uint32_t off, row_regs &b) {
+            const uint8_t *src = add_wide(textl, off); // one multiply-add on the FMA pipe instead of two ALU adds
+            ldg256_if(off < lim, b, src);
+            ldg32_if(lane == 31 && off + UN_GRP < lim, b.la, src + UN_GRP);
+            if (UN_PF) prefetch_l2_if(off + UN_PF * UN_ROW < lim, src + UN_PF * UN_ROW);
         };
-#else
-        auto issue_row = [&](uint32_t r, uint32_t slot) {
-            const uint32_t row = r * UN_ROW;
-            const uint32_t dst = ring_sa + slot * UN_SLOT_BYTES;
-            const uint8_t *src = add_wide(textl, row); // one multiply-add on the FMA pipe instead of two ALU adds
-            if (row + UN_SLOT_BYTES <= load_end) {
-                cp_async16(dst + off0, src);
-                cp_async16(dst + off1, src + 16);
-                if (UN_TAIL) cp_async16_if(lane == 31, dst + offtail, src + 32);
-            } else if (row < e_rel) { // r < nrows
-                const uint32_t g = row + lane * UN_GRP;
-                if (g < load_end) cp_async16(dst + off0, src);
-                if (g + 16 < load_end) cp_async16(dst + off1, src + 16);
-                if (UN_TAIL && lane == 31 && g + 32 < load_end) cp_async16(dst + offtail, src + 32);
-            }
-            cp_async_commit();
-        };
-#endif
-        for (uint32_t r = 0; r < UN_SLOTS; r++) issue_row(r, r);
 
-        // one row: wait for its slot, filter, refill the slot, push the events
-        auto scan_row = [&](const uint32_t r, const uint32_t slot) {
-            cp_async_wait<UN_TAIL ? UN_SLOTS - 1 : UN_SLOTS - 2>();
-            __syncwarp(); // my lookahead is the next lane's copy
-            const uint32_t base = ring_sa + slot * UN_SLOT_BYTES;
-            const uint4 c0 = lds128v(base + off0), c1 = lds128v(base + off1);
-            // the 8 bytes after my group: the next lane's, for lane 31 the first of the next row (next slot)
-            const uint2 la2 = lds64v(UN_TAIL || slot + 1 < UN_SLOTS || lane != 31 ? base + offla : ring_sa);
-            const uint32_t la = la2.x;
+        // one row: filter its bytes, append the events, refill the buffer with the row UN_NBUF ahead, and resolve
+        // 32 events once the list holds that many
+        auto scan_row = [&](const uint32_t off, row_regs &b) {
+            // the 4 bytes after my group: the next lane's first word, for lane 31 the first of the next row
+            const uint32_t la_next = __shfl_down_sync(FULL, b.w[0], 1);
+            const uint32_t la = lane == 31 ? b.la : la_next;
 
-#ifdef KMPB_FILTER6
-            // ---- shift-and filter over 36 bytes, two per update -----------------------------------
-            // Update j takes bytes 2j, 2j+1 and reports the windows that end there, i.e. the starts 2j-3 and 2j-2.
-            // acc[k] collects the starts 0..8, 9..16, 17..24, 25..31 (k = 0 also the NUL bits of bytes 0..2).
-            uint32_t S = F6_ARM, acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-            SA2_WORD(c0.x, acc0); SA2_WORD(c0.y, acc0); SA2_WORD(c0.z, acc0); // bytes 0..11
-            SA2_WORD(c0.w, acc1); SA2_WORD(c1.x, acc1);                       // bytes 12..19
-            SA2_WORD(c1.y, acc2); SA2_WORD(c1.z, acc2);                       // bytes 20..27
-            SA2_WORD(c1.w, acc3);                                             // bytes 28..31
-            // lookahead: starts 29..31 report here; a NUL here is the next lane's, and so is start 32
-            uint32_t accA = 0, accB = 0;
-            SA2_STEP(la, SEL0, SEL1, accA); // bytes 32, 33: starts 29, 30
-            SA2_STEP(la, SEL2, SEL3, accB); // bytes 34, 35: start 31 (bits 24..28) and start 32
-            acc3 |= (accA & 0x1f7c0000u) | (accB & 0x1f000000u);
-            // a quarter's reports of either byte of an update, merged into bits 18..23; byte 2 of that is
-            // (reports << 2): candidate buckets in bits 2..6, NUL in bit 7 -- the layout the rest of the kernel knows
-            acc0 |= acc0 >> 6; acc1 |= acc1 >> 6; acc2 |= acc2 >> 6; acc3 |= acc3 >> 6;
-            const uint32_t tops =
-                __byte_perm(__byte_perm(acc0, acc1, 0x0062), __byte_perm(acc2, acc3, 0x0062), 0x5410) & 0xfcfcfcfcu;
-#else
-            // ---- shift-and filter over 35 bytes ---------------------------------------------------
-            // Reports are collected per quarter of the group: acc[k] covers the steps at which starts
-            // 8k..8k+7 report (and, for k = 0, the three steps before them, for their NUL bits).
-            uint32_t S, acc0, acc1, acc2, acc3, accC;
-            S = LUT_AT(c0.x, SEL0) & 0x808080ffu; // no history: only the NUL stage is pre-armed
-            acc0 = S;
-            SA_STEP(c0.x, SEL1, acc0);
-            SA_STEP(c0.x, SEL2, acc0);
-            SA_STEP(c0.x, SEL3, acc0);
-            SA_WORD(c0.y, acc0);
-            SA_STEP(c0.z, SEL0, acc0);
-            SA_STEP(c0.z, SEL1, acc0);
-            SA_STEP(c0.z, SEL2, acc0);
-            acc1 = 0;
-            SA_STEP(c0.z, SEL3, acc1);
-            SA_WORD(c0.w, acc1);
-            SA_STEP(c1.x, SEL0, acc1);
-            SA_STEP(c1.x, SEL1, acc1);
-            SA_STEP(c1.x, SEL2, acc1);
-            acc2 = 0;
-            SA_STEP(c1.x, SEL3, acc2);
-            SA_WORD(c1.y, acc2);
-            SA_STEP(c1.z, SEL0, acc2);
-            SA_STEP(c1.z, SEL1, acc2);
-            SA_STEP(c1.z, SEL2, acc2);
-            acc3 = 0;
-            SA_STEP(c1.z, SEL3, acc3);
-            SA_WORD(c1.w, acc3);
-            // lookahead: candidate starts 29..31 report here; a NUL here is the next lane's
-            accC = 0;
-            SA_STEP(la, SEL0, accC);
-            SA_STEP(la, SEL1, accC);
-            SA_STEP(la, SEL2, accC);
-            acc3 |= accC & 0x7f000000u;
-            // the four top bytes side by side: quarter k has something to resolve iff byte k is nonzero
-            const uint32_t tops = __byte_perm(__byte_perm(acc0, acc1, 0x0073), __byte_perm(acc2, acc3, 0x0073), 0x5410);
-#endif
+            // ---- shift-and filter over 36 bytes, two per update ---------------------------------------
+            // Update j takes bytes 2j, 2j+1 and reports what starts at 2j-3 (bits 24..29) and 2j-2 (bits 18..23): the
+            // bytes' candidate buckets and "this byte is NUL".  acc[k] collects the starts 0..8, 9..16, 17..24, 25..31.
+            uint32_t S = 0, acc0, acc1, acc2, acc3;
+            SA2(b.w[0], 0);                         // bytes 0, 1: nothing can report yet
+            acc0 = SA2(b.w[0], 2);                  // starts -1 (nothing), 0
+            acc0 |= SA2(b.w[1], 0);
+            acc0 |= SA2(b.w[1], 2);
+            acc0 |= SA2(b.w[2], 0);
+            acc0 |= SA2(b.w[2], 2);                 // 7, 8
+            acc1 = SA2(b.w[3], 0);                  // 9, 10
+            acc1 |= SA2(b.w[3], 2);
+            acc1 |= SA2(b.w[4], 0);
+            acc1 |= SA2(b.w[4], 2);                 // 15, 16
+            acc2 = SA2(b.w[5], 0);                  // 17, 18
+            acc2 |= SA2(b.w[5], 2);
+            acc2 |= SA2(b.w[6], 0);
+            acc2 |= SA2(b.w[6], 2);                 // 23, 24
+            acc3 = SA2(b.w[7], 0);                  // 25, 26
+            acc3 |= SA2(b.w[7], 2);
+            acc3 |= SA2(la, 0);                     // 29, 30
+            SA2(la, 2);                             // 31 | 32: the next lane's
+            acc3 |= S & F6_HI;
+            // The reports of quarter k: byte 3 of acc[k] (b0's, bits 0..5) and byte 2 (b1's, bits 2..7), the four
+            // quarters side by side; quarter k has something to resolve iff byte k of `tops` is nonzero.
+            const uint32_t t3 = __byte_perm(__byte_perm(acc0, acc1, 0x0073), __byte_perm(acc2, acc3, 0x0073), 0x5410);
+            const uint32_t t2 = __byte_perm(__byte_perm(acc0, acc1, 0x0062), __byte_perm(acc2, acc3, 0x0062), 0x5410);
+            const uint32_t tops = (t2 & 0xfcfcfcfcu) | t3;
             const uint32_t m = __ballot_sync(FULL, tops != 0);
-
-            // every lane holds its bytes: refill the slot with the row UN_SLOTS ahead
-            issue_row(r + UN_SLOTS, slot);
 
 #ifdef KMPB_ABLATE_SLOW_PATH // measurement only (wrong counts): how fast is the fast path alone?
             if (m == 0x12345678u)
 #endif
             if (m) {
-                const uint32_t n = __popc(m);
-                auto resolve_pending = [&]() {
-                    drain_events(sc, q_sa, qn, lutlane, mul);
-                    qn = 0;
-                    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sc.scratch_sa + 196), "r"(0u) : "memory"); // nothing older pending
-                };
-                if (qn + n > UN_QCAP) { // the list cannot take this row's events
-                    if (UN_DENSE <= 32 && n >= UN_DENSE) {
-                        // NUL-dense row: its own (rare) path, so that the usual one keeps its registers
-                        const uint32_t tops2 = drop_superseded(tops, m);
-                        const uint32_t m2 = __ballot_sync(FULL, tops2 != 0), n2 = __popc(m2);
-                        if (qn + n2 > UN_QCAP) resolve_pending();
-                        if (tops2 != 0) {
-                            const uint32_t e = q_sa + (qn + __popc(m2 & lt)) * (UN_Q_WORDS * 4);
-#ifdef KMPB_UN_LEAN_EVENTS
-                            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(e + 40), "r"(g32 + (r << 5)), "r"(tops2) : "memory");
-#else
-                            sts128v(e, c0.x, c0.y, c0.z, c0.w);
-                            sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
-                            sts128v(e + 32, la, la2.y, g32 + (r << 5), tops2);
-#endif
-                        }
-                        qn += n2;
-                        return;
-                    }
-                    resolve_pending();
+                uint32_t tp = tops, mp = m;
+                if (UN_DENSE <= 32 && __popc(m) >= (int)UN_DENSE) {
+                    // NUL-dense row: superseded NUL-only events are dropped first (a rare path of its own)
+                    tp = drop_superseded(tops, m, ((t2 & 0x7c7c7c7cu) | (t3 & 0x1f1f1f1fu)) != 0);
+                    mp = __ballot_sync(FULL, tp != 0);
                 }
-                if (tops != 0) {
-                    const uint32_t e = q_sa + (qn + __popc(m & lt)) * (UN_Q_WORDS * 4);
-#ifdef KMPB_UN_LEAN_EVENTS
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(e + 40), "r"(g32 + (r << 5)), "r"(tops) : "memory");
-#else
-                    sts128v(e, c0.x, c0.y, c0.z, c0.w);
-                    sts128v(e + 16, c1.x, c1.y, c1.z, c1.w);
-                    sts128v(e + 32, la, la2.y, g32 + (r << 5), tops);
-#endif
+                // the ring takes it: fewer than 32 events were pending, a row appends at most 32
+                if (tp != 0) {
+                    uint32_t lt;
+                    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+                    const uint32_t e = warp_q_sa() + ((qw + __popc(mp & lt)) & (UN_QCAP - 1)) * UN_Q_BYTES1;
+                    sts128v(e, b.w[0], b.w[1], b.w[2], b.w[3]);
+                    sts128v(e + 16, b.w[4], b.w[5], b.w[6], b.w[7]);
+                    sts128v(e + 32, la, 0u, g32 + (off >> 5), tp);
                 }
-                qn += n;
+                const uint32_t np = __popc(mp);
+                qn += np;
+                qw += np;
+            }
+            // the buffer is free: the row UN_NBUF ahead goes into it
+            load_row(off + UN_NBUF * UN_ROW, b);
+            // with the loads on their way: resolve 32 events if there are that many (no event of the item before this
+            // one is left afterwards: there were fewer than 32 of them when this item was taken)
+            if (qn >= UN_QDRAIN) {
+                resolve_oldest();
+                if (lane == 0) sts32v(warp_scratch_sa() + SC_STATE + 4, 0u);
             }
         };
-#if KMPB_UN_SLOTS == 2
-        // two rows per trip: the slots are compile-time constants, half the loop bookkeeping
-#pragma unroll 1
-        for (uint32_t r = 0; r < nrows; r += 2) {
-            scan_row(r, 0);
-            if (r + 1 < nrows) scan_row(r + 1, 1);
-        }
-#elif KMPB_UN_SLOTS == 3
-#pragma unroll 1
-        for (uint32_t r = 0; r < nrows; r += 3) {
-            scan_row(r, 0);
-            if (r + 1 < nrows) scan_row(r + 1, 1);
-            if (r + 2 < nrows) scan_row(r + 2, 2);
-        }
-#else
-        uint32_t slot = 0;
-#pragma unroll 1
-        for (uint32_t r = 0; r < nrows; r++) {
-            scan_row(r, slot);
-            slot = slot + 1 == UN_SLOTS ? 0 : slot + 1;
-        }
+
+        // the first UN_PF rows' lines: 128 bytes per lane and step
+        if (UN_PF)
+            for (uint32_t x = lane * 128u; x < UN_PF * UN_ROW; x += 4096u) prefetch_l2_if(x < load_end, textl - lane * UN_GRP + x);
+        // UN_NBUF rows per trip: the buffers are compile-time registers, no moves between them
+        row_regs b0 = {}, b1 = {};
+        load_row(0, b0);
+        load_row(UN_ROW, b1);
+#if KMPB_UN_NBUF >= 3
+        row_regs b2 = {};
+        load_row(2 * UN_ROW, b2);
 #endif
+#if KMPB_UN_NBUF >= 4
+        row_regs b3 = {};
+        load_row(3 * UN_ROW, b3);
+#endif
+        uint32_t off = 0;
+#pragma unroll 1
+        for (;;) {
+            scan_row(off, b0);
+            if ((off += UN_ROW) >= e_rel) break;
+            scan_row(off, b1);
+            if ((off += UN_ROW) >= e_rel) break;
+#if KMPB_UN_NBUF >= 3
+            scan_row(off, b2);
+            if ((off += UN_ROW) >= e_rel) break;
+#endif
+#if KMPB_UN_NBUF >= 4
+            scan_row(off, b3);
+            if ((off += UN_ROW) >= e_rel) break;
+#endif
+        }
     }
     // leftovers
-    if (qn) drain_events(sc, q_sa, qn, lutlane, mul);
+    while (qn) resolve_oldest();
 
     __syncthreads();
     if (p.counts_in_smem)
@@ -956,9 +766,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     if (p.n_out) {
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_lut_saddr[1] = atomicAdd(&p.work[2], 1u) == gridDim.x - 1 ? 1u : 0u;
+        if (threadIdx.x == 0) s_misc[0] = atomicAdd(&p.work[2], 1u) == gridDim.x - 1 ? 1u : 0u;
         __syncthreads();
-        if (s_lut_saddr[1]) {
+        if (s_misc[0]) {
             __threadfence();
             for (uint32_t i = threadIdx.x; i < p.n_pat; i += UN_THREADS) {
                 const unsigned long long v = __ldcg(p.uniq_counts + p.pat_to_uniq[i]);
@@ -1013,13 +823,11 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     uint32_t *d_items = ctx->d_items + (size_t)slot * ctx->items_cap;
     uint32_t *d_work = ctx->d_work + slot * 4;
 
-    // the counters go into the shared-memory gap in front of the LUT if they fit, the hash tables behind
-    // the row rings if the block's 227 KB allow it (the LUT may start up to 64 KB into the allocation)
-    uint32_t front = UN_FRONT_FIXED;
-    const bool counts_in_smem = front + 4ull * h.n_uniq + 16 <= UN_FRONT_MAX;
-    if (counts_in_smem) front += (4u * h.n_uniq + 15u) & ~15u;
-    const bool vtab_in_smem = UN_SMEM_BYTES + 4ull * h.vtab_words <= UN_SMEM_MAX;
-    const size_t smem_bytes = UN_SMEM_BYTES + (vtab_in_smem ? 4ull * h.vtab_words : 0);
+    // the counters and the probe tables go into shared memory if the block's 227 KB allow it
+    const bool counts_in_smem = UN_SMEM_FIXED + 4ull * h.n_uniq + 16 <= UN_SMEM_MAX - 8192;
+    const size_t counts_bytes = counts_in_smem ? ((4ull * h.n_uniq + 15) & ~15ull) : 0;
+    const bool vtab_in_smem = UN_SMEM_FIXED + counts_bytes + 4ull * h.vtab_words <= UN_SMEM_MAX;
+    const size_t smem_bytes = UN_SMEM_FIXED + counts_bytes + (vtab_in_smem ? 4ull * h.vtab_words : 0);
     if (!ctx->attr_union_set) {
         KMPB_CUDA(cudaFuncSetAttribute(kmpb_union_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UN_SMEM_MAX));
         ctx->attr_union_set = true;
@@ -1040,14 +848,11 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     p.vtab_in_smem = vtab_in_smem ? 1u : 0u;
     p.vtab = ctx->dev.vtab;
     p.vtab_words = h.vtab_words;
-    p.vtab_one_off = h.vtab[5];
-#ifdef KMPB_FILTER6
-    p.mul256 = 64u;
+    p.vt_slots_a = h.vtab[1]; p.vt_shift_a = h.vtab[2];
+    p.vt_slots_b = h.vtab[3]; p.vt_shift_b = h.vtab[4];
+    p.vt_one = h.vtab[5]; p.vt_rec = h.vtab[6]; p.vt_blob = h.vtab[7];
+    p.mul64 = 64u;
     p.mul4096 = 4096u;
-#else
-    p.mul256 = 256u;
-    p.mul4096 = 0u;
-#endif
     p.uniq_counts = (unsigned long long *)d_uniq_counts;
     p.pat_to_uniq = ctx->dev.pat_to_uniq;
     p.n_pat = h.n_pat;

@@ -279,8 +279,10 @@ int kmpb_filter6_build(const kmpb_tables *t, uint32_t words[256], double *estima
     }
     const double e = build_filter_words(t->n_uniq, uniq, 5, 6, words);
     free(uniq);
-    for (uint32_t c = 0; c < 256; c++) words[c] |= (0x3fu << 24) | (1u << 5) | (1u << 11) | (1u << 17);
-    words[0] |= 1u << 23;
+    /* the NUL detector: depth 0 passes on NUL only, depths 1..3 always -- it reports three bytes after the NUL, when a
+     * pattern starting at the NUL would report, so that a report's "candidate" and "NUL" bits speak of the same byte */
+    for (uint32_t c = 0; c < 256; c++) words[c] |= (0x3fu << 24) | (1u << 11) | (1u << 17) | (1u << 23);
+    words[0] |= 1u << 5;
     if (estimate) *estimate = e;
     return KMPB_OK;
 }
@@ -394,8 +396,9 @@ static int build_dfa(kmpb_tables *t)
 
 #define VT_HEADER 8
 
-/* slot of a text position's first two bytes (little-endian u16) in a table of 1 << (32 - shift) slots */
-uint32_t kmpb_vtab_slot(uint32_t first2, uint32_t shift) { return ((first2 & 0xffffu) * 0x9e3779b1u) >> shift; }
+/* slot of a text position's first bytes (little-endian, masked to the key length by the caller) in a table of
+ * 1 << (32 - shift) slots */
+uint32_t kmpb_vtab_slot(uint32_t key, uint32_t shift) { return (key * 0x9e3779b1u) >> shift; }
 
 static uint32_t word_of(const uint8_t *p, uint32_t len, uint32_t from)
 {
@@ -410,50 +413,62 @@ static uint32_t mask_of(uint32_t len, uint32_t from)
     return k;
 }
 
+/* key of a pattern in its probe table: A = the two-byte patterns (their two bytes), B = three and more bytes
+ * (the first three) */
+static uint32_t vt_key(const uint8_t *p, uint32_t len) { return word_of(p, len < 3 ? len : 3, 0); }
+
 static int build_verify_tables(kmpb_tables *t)
 {
-    /* one slot per hash value of a pattern's first two bytes; at least four slots per pattern of two or more bytes,
-     * so most slots are empty and most occupied slots hold the patterns of a single two-byte prefix */
-    uint32_t n2 = 0, n1 = 0, blob_words = 0;
+    /* Two probe tables, one slot per hash value of the key, at least four slots per pattern: most slots are empty and
+     * most occupied slots hold the patterns of a single key.  Keying the longer patterns by three bytes instead of two
+     * (round 1) cuts the longest chain of strings.txt from 6 records ("se..") to 3 ("htt", "por") -- a warp walks as
+     * many records as its longest chain. */
+    uint32_t n_a = 0, n_b = 0, n1 = 0, blob_words = 0;
     for (uint32_t u = 0; u < t->n_uniq; u++) {
-        if (t->uniq_len[u] >= 2) n2++; else n1++;
+        if (t->uniq_len[u] >= 3) n_b++; else if (t->uniq_len[u] == 2) n_a++; else n1++;
         blob_words += (t->uniq_len[u] + 3) / 4;
     }
-    uint32_t log_slots = 6;
-    while (log_slots < 16 && (1u << log_slots) < 4 * n2) log_slots++;
-    const uint32_t slots = 1u << log_slots, shift = 32 - log_slots;
+    uint32_t log_a = 4, log_b = 6;
+    while (log_a < 16 && (1u << log_a) < 4 * n_a) log_a++;
+    while (log_b < 20 && (1u << log_b) < 4 * n_b) log_b++;
+    const uint32_t slots_a = n_a ? 1u << log_a : 0, slots_b = n_b ? 1u << log_b : 0;
     uint32_t at = VT_HEADER;
-    const uint32_t slot_off = at;
-    at += 2 * slots;
+    const uint32_t slot_a_off = n_a ? at : 0;
+    at += 2 * slots_a;
+    const uint32_t slot_b_off = n_b ? at : 0;
+    at += 2 * slots_b;
     const uint32_t one_off = n1 ? at : 0;
     if (n1) at += 256;
     at = (at + 3u) & ~3u; /* records are read 16 bytes at a time */
     const uint32_t rec_off = at;
-    at += 8 * n2;
+    at += 8 * (n_a + n_b);
     const uint32_t blob_off = at;
     at += blob_words;
     uint32_t *v = calloc(at ? at : 1, sizeof *v);
-    uint32_t *fill = calloc(slots, sizeof *fill);
+    uint32_t *fill = calloc((size_t)slots_a + slots_b + 1, sizeof *fill);
     if (!v || !fill) { free(v); free(fill); return kmpb_fail(KMPB_ENOMEM, "out of memory building the verification tables"); }
-    v[0] = at; v[1] = slot_off; v[2] = shift; v[3] = rec_off; v[4] = blob_off; v[5] = one_off;
+    v[0] = at; v[1] = slot_a_off; v[2] = 32 - log_a; v[3] = slot_b_off; v[4] = 32 - log_b; v[5] = one_off;
+    v[6] = rec_off; v[7] = blob_off;
     for (uint32_t i = 0; n1 && i < 256; i++) v[one_off + i] = 0xffffffffu;
-    /* chain lengths, then chain starts (records of one slot are contiguous) */
+    /* chain lengths, then chain starts (records of one slot are contiguous; table A's records come first) */
     for (uint32_t u = 0; u < t->n_uniq; u++) {
         const uint8_t *p = t->uniq_blob + t->uniq_off[u];
-        if (t->uniq_len[u] >= 2) v[slot_off + 2 * kmpb_vtab_slot(p[0] | (uint32_t)p[1] << 8, shift) + 1]++;
+        const uint32_t len = t->uniq_len[u];
+        if (len >= 3) v[slot_b_off + 2 * kmpb_vtab_slot(vt_key(p, len), 32 - log_b) + 1]++;
+        else if (len == 2) v[slot_a_off + 2 * kmpb_vtab_slot(vt_key(p, len), 32 - log_a) + 1]++;
     }
-    for (uint32_t s = 0, first = 0; s < slots; s++) {
-        v[slot_off + 2 * s] = first;
-        first += v[slot_off + 2 * s + 1];
-    }
+    uint32_t first = 0;
+    for (uint32_t s = 0; s < slots_a; s++) { v[slot_a_off + 2 * s] = first; first += v[slot_a_off + 2 * s + 1]; }
+    for (uint32_t s = 0; s < slots_b; s++) { v[slot_b_off + 2 * s] = first; first += v[slot_b_off + 2 * s + 1]; }
     uint32_t bw = 0;
     for (uint32_t u = 0; u < t->n_uniq; u++) {
         const uint8_t *p = t->uniq_blob + t->uniq_off[u];
         const uint32_t len = t->uniq_len[u];
         memcpy((uint8_t *)(v + blob_off + bw), p, len); /* rest of the last word stays zero */
         if (len >= 2) {
-            const uint32_t s = kmpb_vtab_slot(p[0] | (uint32_t)p[1] << 8, shift);
-            uint32_t *rec = v + rec_off + 8 * (v[slot_off + 2 * s] + fill[s]++);
+            const uint32_t s = len >= 3 ? kmpb_vtab_slot(vt_key(p, len), 32 - log_b) : kmpb_vtab_slot(vt_key(p, len), 32 - log_a);
+            const uint32_t so = len >= 3 ? slot_b_off : slot_a_off, fi = len >= 3 ? slots_a + s : s;
+            uint32_t *rec = v + rec_off + 8 * (v[so + 2 * s] + fill[fi]++);
             rec[0] = word_of(p, len, 0); rec[1] = mask_of(len, 0);
             rec[2] = word_of(p, len, 4); rec[3] = mask_of(len, 4);
             rec[4] = len; rec[5] = u; rec[6] = bw; rec[7] = 0;
@@ -471,6 +486,13 @@ static int build_verify_tables(kmpb_tables *t)
 /* ---- entry points ----------------------------------------------------------------------------- */
 
 int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat)
+{
+    return kmpb_tables_build_ex(t, blob, pat_off, n_pat, 0);
+}
+
+/* with_dfa != 0 also builds the merged automaton of all patterns (next / trie / out_*): the reference the table tests
+ * check the filter and the verification tables against.  The device never sees it, so the library does not build it. */
+int kmpb_tables_build_ex(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat, int with_dfa)
 {
     memset(t, 0, sizeof *t);
     if (n_pat && (blob == NULL || pat_off == NULL)) return kmpb_fail(KMPB_EINVAL, "kmpb_set_patterns: NULL pattern data");
@@ -527,9 +549,12 @@ int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_o
     t->n_uniq = nu;
     free(refs);
 
-    int rc = build_dfa(t);
+    int rc = with_dfa ? build_dfa(t) : KMPB_OK;
     if (rc == KMPB_OK) rc = build_verify_tables(t);
-    if (rc == KMPB_OK) build_filter(t, uniq);
+    if (rc == KMPB_OK) {
+        build_filter(t, uniq);
+        rc = kmpb_filter6_build(t, t->filter6, &t->filter6_fp_estimate);
+    }
     free(uniq);
     if (rc != KMPB_OK) kmpb_tables_free(t);
     return rc;

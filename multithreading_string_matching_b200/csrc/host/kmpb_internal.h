@@ -50,13 +50,21 @@ typedef struct kmpb_tables {
     uint32_t filter[256];
     uint32_t bucket_of_uniq_valid; /* 1 when filter[] is usable (n_uniq > 0) */
 
-    /* start-anchored verification tables (the device's slow path): the patterns of two or more bytes, grouped by
-     * the hash of their first two bytes; a text position probes one slot and compares the records of that slot.
+    /* the same prefilter in the geometry the union kernel uses (automaton.c kmpb_filter6_build): five fields of 6 bits
+     * (depths 0..3 and a field in which a report lingers one step), 5 pattern buckets + the NUL detector, so that the
+     * kernel updates its state once per two bytes */
+    uint32_t filter6[256];
+    double filter6_fp_estimate;
+
+    /* start-anchored verification tables (the device's slow path): two probe tables -- A for the two-byte patterns,
+     * keyed by their two bytes, B for the patterns of three and more bytes, keyed by their first three -- of slots
+     * {first record, records}; a text position probes one slot of each and compares the records of those slots.
      * Layout of vtab (u32 words):
-     *   [0] total words   [1] word offset of the slots   [2] hash shift (slots = 1 << (32 - shift))
-     *   [3] word offset of the records   [4] word offset of the pattern words
+     *   [0] total words
+     *   [1] word offset of the slots of A (0 = no two-byte patterns)   [2] hash shift of A (slots = 1 << (32 - shift))
+     *   [3] word offset of the slots of B (0 = none)                   [4] hash shift of B
      *   [5] word offset of the one-byte patterns' table (256 words: distinct id or 0xffffffff), 0 = there are none
-     *   slots: 2 words {first record, number of records} -- the patterns whose first two bytes hash to this slot
+     *   [6] word offset of the records   [7] word offset of the pattern words
      *   records (8 words, 16-byte aligned): {pattern bytes 0..3, mask of those that exist, bytes 4..7, their mask,
      *            length, distinct id, word offset of the pattern's bytes inside the pattern words, 0}
      *   pattern words: every pattern zero-padded to a multiple of 4 bytes */
@@ -72,9 +80,11 @@ uint64_t kmpb_pcap_chunk_end(const kmpb_pcap *pc, uint64_t first, uint64_t last,
                              uint64_t *bytes_out);
 void kmpb_pcap_pack(const kmpb_pcap *pc, uint64_t first, uint64_t count, uint8_t *dst, uint64_t *offsets);
 
-/* slot of a text position's first two bytes in the verification tables (the device uses the same expression) */
-uint32_t kmpb_vtab_slot(uint32_t first2, uint32_t shift);
+/* slot of a key (a text position's first two or three bytes) in a probe table (the device uses the same expression) */
+uint32_t kmpb_vtab_slot(uint32_t key, uint32_t shift);
 int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat);
+/* ... and, with_dfa != 0, the merged automaton of all patterns the table tests compare against (never uploaded) */
+int kmpb_tables_build_ex(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat, int with_dfa);
 /* the prefilter in 6-bit fields (5 pattern buckets + NUL, depth 4 + a lingering field): automaton.c, DESIGN.md section 10 */
 int kmpb_filter6_build(const kmpb_tables *t, uint32_t words[256], double *estimate);
 void kmpb_tables_free(kmpb_tables *t);

@@ -5,7 +5,9 @@
  *      (the property that makes the union automaton a drop-in for P independent kmp_matcher calls);
  *   2. the shift-and prefilter never misses: for every true occurrence starting at s the filter word
  *      after byte s+3 (text padded with zero bytes) has one of bits 24..30 set;
- *   3. bit 31 of the filter word is set exactly on NUL bytes.
+ *   3. bit 31 of the filter word is set exactly on NUL bytes;
+ *   4. the same for the filter in 6-bit fields the union kernel uses (two bytes per update), whose NUL detector
+ *      reports three bytes late (when a pattern starting at the NUL would report).
  * Exit status 0 = all good.  Built and run by tests/test_host.py.
  */
 #include <stdio.h>
@@ -48,7 +50,7 @@ static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int
     }
 
     kmpb_tables t;
-    if (kmpb_tables_build(&t, blob, off, (uint32_t)n_pat) != 0) { fprintf(stderr, "build failed: %s\n", kmpb_last_error()); return 1; }
+    if (kmpb_tables_build_ex(&t, blob, off, (uint32_t)n_pat, 1) != 0) { fprintf(stderr, "build failed: %s\n", kmpb_last_error()); return 1; }
 
     /* 1. DFA counts (NULs are ordinary mismatching bytes here: class 0) */
     uint64_t *got = calloc((size_t)t.n_uniq + 1, sizeof *got);
@@ -75,32 +77,41 @@ static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int
     for (uint32_t u = 0; u < t.n_uniq; u++)
         if (got_trie[u] != got[u]) { fprintf(stderr, "uniq %u: trie %llu dfa %llu\n", u, (unsigned long long)got_trie[u], (unsigned long long)got[u]); bad = 1; }
     free(got_trie);
-    /* 1c. the verification tables, probed at every start position the way the device probes them (one slot per
-     *     position, masked compare of the first 8 bytes, then the remaining pattern words), report the same counts */
+    /* 1c. the probe tables, probed at every start position the way the device probes them (one slot of table A by the
+     *     first two bytes, one of table B by the first three, masked compare of the first 8 bytes, then the remaining
+     *     pattern words), report the same counts */
     if (t.n_uniq) {
         const uint32_t *v = t.vtab;
         uint64_t *got_hash = calloc((size_t)t.n_uniq + 1, sizeof *got_hash);
         uint32_t n_rec = 0;
-        for (uint32_t s = 0; s < (1u << (32 - v[2])); s++) {
-            if (v[v[1] + 2 * s] != n_rec) { fprintf(stderr, "slot %u: chains are not contiguous\n", s); bad = 1; }
-            n_rec += v[v[1] + 2 * s + 1];
+        for (int tab = 0; tab < 2; tab++) {
+            const uint32_t so = v[1 + 2 * tab], shift = v[2 + 2 * tab];
+            if (!so) continue;
+            for (uint32_t s = 0; s < (1u << (32 - shift)); s++) {
+                if (v[so + 2 * s] != n_rec) { fprintf(stderr, "table %d slot %u: chains are not contiguous\n", tab, s); bad = 1; }
+                n_rec += v[so + 2 * s + 1];
+            }
         }
         for (int s = 0; s < text_len; s++) {
             uint32_t x0 = 0, x1 = 0;
             for (int k = 0; k < 4; k++) x0 |= (uint32_t)text[s + k] << (8 * k); /* text is zero padded */
             for (int k = 0; k < 4; k++) x1 |= (uint32_t)text[s + 4 + k] << (8 * k);
             if (v[5] && v[v[5] + (x0 & 0xffu)] != 0xffffffffu) got_hash[v[v[5] + (x0 & 0xffu)]]++;
-            const uint32_t *e = v + v[1] + 2 * kmpb_vtab_slot(x0, v[2]);
-            for (uint32_t r = 0; r < e[1]; r++) {
-                const uint32_t *rec = v + v[3] + 8 * (e[0] + r);
-                const uint32_t len = rec[4], u = rec[5];
-                const uint8_t *pb = (const uint8_t *)(v + v[4] + rec[6]);
-                if (u >= t.n_uniq || len != t.uniq_len[u] || len < 2 || memcmp(pb, t.uniq_blob + t.uniq_off[u], len)) { fprintf(stderr, "record of slot: wrong pattern\n"); bad = 1; break; }
-                if (((x0 ^ rec[0]) & rec[1]) | ((x1 ^ rec[2]) & rec[3])) continue;
-                if (s + (int)len > text_len) continue;
-                if (len > 8 && memcmp(text + s + 8, pb + 8, len - 8)) continue;
-                if (memcmp(text + s, pb, len)) { fprintf(stderr, "record masks wrong for uniq %u\n", u); bad = 1; }
-                got_hash[u]++;
+            for (int tab = 0; tab < 2; tab++) {
+                const uint32_t so = v[1 + 2 * tab], shift = v[2 + 2 * tab];
+                if (!so) continue;
+                const uint32_t *e = v + so + 2 * kmpb_vtab_slot(x0 & (tab ? 0xffffffu : 0xffffu), shift);
+                for (uint32_t r = 0; r < e[1]; r++) {
+                    const uint32_t *rec = v + v[6] + 8 * (e[0] + r);
+                    const uint32_t len = rec[4], u = rec[5];
+                    const uint8_t *pb = (const uint8_t *)(v + v[7] + rec[6]);
+                    if (u >= t.n_uniq || len != t.uniq_len[u] || (tab ? len < 3 : len != 2) || memcmp(pb, t.uniq_blob + t.uniq_off[u], len)) { fprintf(stderr, "record of slot: wrong pattern\n"); bad = 1; break; }
+                    if (((x0 ^ rec[0]) & rec[1]) | ((x1 ^ rec[2]) & rec[3])) continue;
+                    if (s + (int)len > text_len) continue;
+                    if (len > 8 && memcmp(text + s + 8, pb + 8, len - 8)) continue;
+                    if (memcmp(text + s, pb, len)) { fprintf(stderr, "record masks wrong for uniq %u\n", u); bad = 1; }
+                    got_hash[u]++;
+                }
             }
         }
         for (uint32_t u = 0; u < t.n_uniq; u++)
@@ -122,35 +133,32 @@ static int run_case(int n_pat, int max_len, const char *alpha, int text_len, int
             if (!(S & 0x7f000000u)) { fprintf(stderr, "filter missed pattern %d at %d\n", p, s); bad = 1; }
         }
     }
-    /* 2b. the same filter in 6-bit fields (kmpb_filter6_build: 5 buckets + NUL, depth 4 + a lingering field), as a
-     *     two-bytes-per-update kernel would use it: superset of the true occurrences, NUL bit exact, the report of
-     *     the previous byte lingering in bits 24..29, and the two-byte update equal to two one-byte updates */
+    /* 4. the filter in 6-bit fields (t.filter6: 5 buckets + NUL, depth 4 + a lingering field), as the union kernel uses
+     *    it: superset of the true occurrences; bit 23 after the update of byte i says "byte i-3 is NUL" (exactly); the
+     *    report of the previous byte lingers in bits 24..29; the two-byte update equals two one-byte updates */
     {
-        uint32_t w6[256];
-        double est6 = 0;
-        if (kmpb_filter6_build(&t, w6, &est6) != 0) { fprintf(stderr, "filter6 build failed\n"); return 1; }
-        const uint32_t arm = (1u << 5) | (1u << 11) | (1u << 17), all30 = 0x3fffffffu;
+        const uint32_t *w6 = t.filter6;
+        const uint32_t all30 = 0x3fffffffu;
         for (int p = 0; p < n_pat; p++) {
             int len = (int)(off[p + 1] - off[p]);
             for (int s0 = 0; s0 + len <= text_len; s0++) {
                 if (memcmp(text + s0, blob + off[p], (size_t)len)) continue;
-                uint32_t S6 = arm;
+                uint32_t S6 = 0;
                 for (int k = 0; k < 4; k++) S6 = ((S6 << 6) | 0x3fu) & w6[text[s0 + k]]; /* text is zero padded */
                 if (!(S6 & (0x1fu << 18))) { fprintf(stderr, "filter6 missed pattern %d at %d\n", p, s0); bad = 1; }
             }
         }
-        uint32_t S1 = arm, S2 = arm;
+        uint32_t S1 = 0, S2 = 0;
         for (int i = 0; i + 1 < text_len; i += 2) {
             const uint32_t b0 = text[i], b1 = text[i + 1];
             const uint32_t mid = ((S1 << 6) | 0x3fu) & w6[b0];
-            if (((mid >> 23) & 1u) != (b0 == 0)) { fprintf(stderr, "filter6 NUL bit wrong at %d\n", i); bad = 1; break; }
+            if (i >= 3 && ((mid >> 23) & 1u) != (text[i - 3] == 0)) { fprintf(stderr, "filter6 NUL bit wrong at %d\n", i); bad = 1; break; }
             S1 = ((mid << 6) | 0x3fu) & w6[b1];
-            if (((S1 >> 23) & 1u) != (b1 == 0)) { fprintf(stderr, "filter6 NUL bit wrong at %d\n", i + 1); bad = 1; break; }
+            if (i >= 2 && ((S1 >> 23) & 1u) != (text[i - 2] == 0)) { fprintf(stderr, "filter6 NUL bit wrong at %d\n", i + 1); bad = 1; break; }
             if (((S1 >> 24) & 0x3fu) != ((mid >> 18) & 0x3fu)) { fprintf(stderr, "filter6: report does not linger at %d\n", i); bad = 1; break; }
             S2 = ((S2 << 12) | 0xfffu) & ((w6[b0] << 6) | 0x3fu) & w6[b1];
             if ((S1 & all30) != (S2 & all30)) { fprintf(stderr, "filter6: two-byte update differs at %d\n", i); bad = 1; break; }
         }
-        (void)est6;
     }
     /* 3. NUL detector */
     uint32_t S = 0x00808080u;
