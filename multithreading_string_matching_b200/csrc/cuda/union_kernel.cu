@@ -92,8 +92,9 @@ constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_BYTES1;
 constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
 constexpr uint32_t UN_OFF_Q = 2 * UN_LUT_BYTES;
 constexpr uint32_t UN_OFF_SCRATCH = UN_OFF_Q + UN_Q_BYTES;
-constexpr uint32_t UN_OFF_MISC = UN_OFF_SCRATCH + UN_SCRATCH_BYTES; // 16 bytes: the "I am the last block" flag
-constexpr uint32_t UN_OFF_COUNTS = UN_OFF_MISC + 16;
+constexpr uint32_t UN_OFF_MISC = UN_OFF_SCRATCH + UN_SCRATCH_BYTES; // 128 bytes: what the resolve step reads of the
+                                                                    // launch parameters (DC_*), the "last block" flag
+constexpr uint32_t UN_OFF_COUNTS = UN_OFF_MISC + 128;
 constexpr size_t UN_SMEM_FIXED = UN_OFF_COUNTS;
 constexpr size_t UN_SMEM_MAX = 227 * 1024; // opt-in shared memory of one block on sm_100
 static_assert(UN_SMEM_FIXED + 16384 <= UN_SMEM_MAX, "shared memory budget");
@@ -175,10 +176,9 @@ __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets
 }
 
 // ---- helpers -----------------------------------------------------------------------------------
-// One row buffer of a lane: its 32 bytes of a row and -- meaningful in lane 31 only -- the 4 bytes after the row.
+// One row buffer of a lane: its 32 bytes of a row.
 struct row_regs {
     uint32_t w[8];
-    uint32_t la;
 };
 // 32 bytes global -> registers in one instruction (SASS LDG.E.256, sm_100), L1 not allocated (the row is used once),
 // under a predicate; a lane that does not load keeps what its registers held (an older row of the same item,
@@ -190,13 +190,15 @@ __device__ __forceinline__ void ldg256_if(bool on, row_regs &b, const void *src)
                  : "+r"(b.w[0]), "+r"(b.w[1]), "+r"(b.w[2]), "+r"(b.w[3]), "+r"(b.w[4]), "+r"(b.w[5]), "+r"(b.w[6]), "+r"(b.w[7])
                  : "l"(src), "r"((uint32_t)on));
 }
-// 4 bytes under a predicate (lane 31's lookahead)
-__device__ __forceinline__ void ldg32_if(bool on, uint32_t &v, const void *src)
+// 4 bytes under a predicate (lane 31's lookahead); 0 otherwise
+__device__ __forceinline__ uint32_t ldg32_if(bool on, const void *src)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t"
+    uint32_t v;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, 0;\n\t"
                  "@p ld.global.L1::no_allocate.u32 %0, [%1];\n\t}"
-                 : "+r"(v)
+                 : "=&r"(v)
                  : "l"(src), "r"((uint32_t)on));
+    return v;
 }
 // the 128-byte line at src on its way into L2 (SASS CCTL.E.PF2): no registers, no wait
 __device__ __forceinline__ void prefetch_l2_if(bool on, const void *src)
@@ -221,6 +223,13 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr)
 {
     uint32_t v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+// the same address in table G (one table further on): an immediate offset, no second base register
+__device__ __forceinline__ uint32_t lds32_g(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+32768];" : "=r"(v) : "r"(saddr));
     return v;
 }
 __device__ __forceinline__ uint2 lds64(uint32_t saddr)
@@ -274,54 +283,68 @@ __device__ __forceinline__ uint32_t clamp32(int32_t x) { return (uint32_t)min(ma
 // filter words of byte k (0..3) of `word`: the IDP.4A builds the whole shared address, byte * 128 + the lane's base
 // in table L (lutL) or G (lutG)
 #define LUT_L(word, k) lds32(__dp4a((uint32_t)(word), 0x80u << (8 * (k)), lutL))
-#define LUT_G(word, k) lds32(__dp4a((uint32_t)(word), 0x80u << (8 * (k)), lutG))
+#define LUT_G(word, k) lds32_g(__dp4a((uint32_t)(word), 0x80u << (8 * (k)), lutL))
 // one two-byte update: bytes k0, k1 = k0 + 1 of `word`
 #define SA2(word, k0) (S = (S * mul2 + 4095u) & LUT_G(word, k0) & LUT_L(word, (k0) + 1))
 // one one-byte update (the resolve step's re-run)
 #define SA1(word, k) (S = (S * mul1 + 63u) & LUT_L(word, k))
 
+// The launch parameters the resolve step reads, copied to shared memory once per block (word indices in the block at
+// UN_OFF_MISC): a function that is not inlined would reach the kernel's parameter space through generic loads.
+enum { DC_TEXT_LO = 0, DC_TEXT_HI,   // p.bytes - p.abs_base: absolute byte 0
+       DC_OFF_LO, DC_OFF_HI,     // p.offsets
+       DC_VTAB_LO, DC_VTAB_HI,   // p.vtab (global)
+       DC_CNT_LO, DC_CNT_HI,     // p.uniq_counts
+       DC_SLOTS_A, DC_SHIFT_A, DC_SLOTS_B, DC_SHIFT_B, DC_ONE, DC_REC, DC_BLOB,
+       DC_MUL64, DC_VTAB_SA,     // shared address of the probe tables, 0 = they are in global memory
+       DC_COUNTS_SA,             // shared address of the counters, 0 = global atomics
+       DC_LAST = 31 };           // "I am the last block" flag
+
 // The scratch words of a warp (128 bytes): two sets of 32 bytes, one per item parity --
-//   {ks, ke, b_rel, e_rel, row0 lo, row0 hi, carry, packets per byte}: the item's packets [ks, ke), its bytes
+//   {ks, ke, b_rel, e_rel, row0 lo, row0 hi, carry, packet size}: the item's packets [ks, ke), its bytes
 //   [b_rel, e_rel) relative to row0 = the absolute position of its first row, 1 + the (relative) position of the last
-//   NUL byte among its events resolved so far (0: none), and (ke - ks) / (e_rel - b_rel) as a float --
+//   NUL byte among its events resolved so far (0: none), and either 0x80000000 | L when all its packets have L bytes or
+//   (ke - ks) / (e_rel - b_rel) as a float (the interpolation guess of the packet lookup) --
 // then, at byte 64, {parity of the item being scanned, "the list holds events of the item before it"}.
 constexpr uint32_t SC_STATE = 64;
+
+extern __shared__ __align__(1024) uint8_t smem[];
+// shared address of the dynamic shared memory (uniform registers; the generic-to-shared conversion costs more)
+__device__ __forceinline__ uint32_t smem_sa()
+{
+    uint32_t a;
+    asm("mov.u32 %0, smem;" : "=r"(a));
+    return a;
+}
+__device__ __forceinline__ uint32_t dc(uint32_t k) { return lds32(smem_sa() + UN_OFF_MISC + 4u * k); }
+__device__ __forceinline__ const uint8_t *dc_ptr(uint32_t k)
+{
+    const uint2 v = lds64(smem_sa() + UN_OFF_MISC + 4u * k);
+    return reinterpret_cast<const uint8_t *>(((uint64_t)v.y << 32) | v.x);
+}
+__device__ __forceinline__ uint32_t warp_q_sa() { return smem_sa() + UN_OFF_Q + (threadIdx.x >> 5) * (UN_QCAP * UN_Q_BYTES1); }
+__device__ __forceinline__ uint32_t warp_scratch_sa() { return smem_sa() + UN_OFF_SCRATCH + (threadIdx.x >> 5) * 128; }
 
 // what a resolve step needs besides the events; every warp derives it from its own index (nothing of it has to live in
 // the row loop's registers)
 struct drain_args {
     uint32_t q_sa;       // the warp's event ring
     uint32_t scratch_sa; // the warp's scratch words
-    uint32_t lutL;       // the lane's base in table L
-    uint32_t vtab_sa;    // the probe tables in shared memory (vtab_in_smem)
+    uint32_t vtab_sa;    // the probe tables in shared memory, 0 = in global memory
     uint32_t counts_sa;  // the shared counters, or 0
 };
-extern __shared__ __align__(1024) uint8_t smem[];
-__device__ __forceinline__ uint32_t warp_q_sa() { return saddr_of(smem + UN_OFF_Q) + (threadIdx.x >> 5) * (UN_QCAP * UN_Q_BYTES1); }
-__device__ __forceinline__ uint32_t warp_scratch_sa() { return saddr_of(smem + UN_OFF_SCRATCH) + (threadIdx.x >> 5) * 128; }
-__device__ __forceinline__ drain_args make_drain_args(const union_params &p)
-{
-    drain_args d;
-    d.q_sa = warp_q_sa();
-    d.scratch_sa = warp_scratch_sa();
-    d.lutL = saddr_of(smem) + ((threadIdx.x & 31) << 2);
-    const uint32_t counts_bytes = p.counts_in_smem ? ((4u * p.n_uniq + 15u) & ~15u) : 0u;
-    d.vtab_sa = saddr_of(smem + UN_OFF_COUNTS) + counts_bytes;
-    d.counts_sa = p.counts_in_smem ? saddr_of(smem + UN_OFF_COUNTS) : 0u;
-    return d;
-}
 
-__device__ __forceinline__ void count_hit(const union_params &p, const drain_args &d, uint32_t u)
+__device__ __forceinline__ void count_hit(const drain_args &d, uint32_t u)
 {
     if (d.counts_sa) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(d.counts_sa + 4u * u) : "memory");
-    else atomicAdd(p.uniq_counts + u, 1ull);
+    else atomicAdd(reinterpret_cast<unsigned long long *>(const_cast<uint8_t *>(dc_ptr(DC_CNT_LO))) + u, 1ull);
 }
 
 // 4 text bytes starting at byte `pos` of the event at entry_sa, of which the first `need` (>= 1) matter: from
 // the event while its 36 bytes last, then from global memory (never past the word that holds the last
 // needed byte, which lies inside the packet).  Where the event's group lies in global memory follows from its
 // group index and its item's row0 in the warp's scratch words.
-__device__ __forceinline__ uint32_t text_window(const union_params &p, const drain_args &d, uint32_t entry_sa, uint32_t pos, uint32_t need)
+__device__ __forceinline__ uint32_t text_window(const drain_args &d, uint32_t entry_sa, uint32_t pos, uint32_t need)
 {
     if (pos + 4 <= 36) {
         const uint32_t a = entry_sa + (pos & ~3u);
@@ -329,7 +352,7 @@ __device__ __forceinline__ uint32_t text_window(const union_params &p, const dra
     }
     const uint32_t meta = lds32v(entry_sa + 40);
     const uint2 r0 = lds64v(d.scratch_sa + ((meta >> 31) << 5) + 16);
-    const uint8_t *gw = p.bytes + ((((uint64_t)r0.y << 32) | r0.x) - p.abs_base) + ((meta & 0x7fffffffu) << 5) + (pos & ~3u);
+    const uint8_t *gw = dc_ptr(DC_TEXT_LO) + (((uint64_t)r0.y << 32) | r0.x) + ((meta & 0x7fffffffu) << 5) + (pos & ~3u);
     const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(gw));
     const uint32_t hi = (pos & 3u) + (need < 4 ? need : 4u) > 4u ? __ldg(reinterpret_cast<const uint32_t *>(gw) + 1) : 0u;
     return __funnelshift_r(lo, hi, 8u * (pos & 3u));
@@ -340,31 +363,38 @@ __device__ __forceinline__ uint32_t text_window(const union_params &p, const dra
 // three one slot of table B (the longer ones); the slots' records carry the pattern's first 8 bytes and their masks,
 // so a record costs one 16-byte load and one masked compare, and only a record that agrees on those bytes is looked
 // at further.
+// where the probe tables' parts are, read once per resolve step
+struct probe_consts {
+    uint32_t slots_a, shift_a, slots_b, shift_b, one, rec;
+};
 template <bool VS>
-__device__ __forceinline__ void verify_start(const union_params &p, const drain_args &d, uint32_t entry_sa, uint32_t i, uint32_t room)
+__device__ __forceinline__ void verify_start(const drain_args &d, const probe_consts &pc, uint32_t entry_sa, uint32_t i, uint32_t room)
 {
-    auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(d.vtab_sa + 4u * word) : __ldg(p.vtab + word); };
+    const uint32_t *vtab_g = VS ? nullptr : reinterpret_cast<const uint32_t *>(dc_ptr(DC_VTAB_LO));
+    auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(d.vtab_sa + 4u * word) : __ldg(vtab_g + word); };
     auto vt4 = [&](uint32_t word) -> uint4 {
-        return VS ? lds128(d.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint4 *>(p.vtab + word));
+        return VS ? lds128(d.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint4 *>(vtab_g + word));
     };
     auto vt2 = [&](uint32_t word) -> uint2 {
-        return VS ? lds64(d.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(p.vtab + word));
+        return VS ? lds64(d.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(vtab_g + word));
     };
-    // text bytes i..i+3 (i + 4 <= 36) and, if a pattern that long fits at all, i+4..i+7
-    const uint32_t x0 = text_window(p, d, entry_sa, i, 4);
-    if (p.vt_one) { // one-byte patterns: a direct table (room >= 1 always holds)
-        const uint32_t u = vt(p.vt_one + (x0 & 0xffu));
-        if (u != 0xffffffffu) count_hit(p, d, u);
+    const uint32_t vt_one = pc.one, vt_slots_a = pc.slots_a, vt_slots_b = pc.slots_b;
+    // text bytes i..i+3 (always inside the event: i + 4 <= 36) and, if a pattern that long fits at all, i+4..i+7
+    const uint32_t x0 = __funnelshift_r(lds32v(entry_sa + (i & ~3u)), lds32v(entry_sa + (i & ~3u) + 4), 8u * (i & 3u));
+    if (vt_one) { // one-byte patterns: a direct table (room >= 1 always holds)
+        const uint32_t u = vt(vt_one + (x0 & 0xffu));
+        if (u != 0xffffffffu) count_hit(d, u);
     }
     if (room < 2) return;
     uint2 ea = make_uint2(0, 0), eb = make_uint2(0, 0); // {first record, records}
-    if (p.vt_slots_a) ea = vt2(p.vt_slots_a + 2u * (((x0 & 0xffffu) * 0x9e3779b1u) >> p.vt_shift_a));
-    if (p.vt_slots_b && room >= 3) eb = vt2(p.vt_slots_b + 2u * (((x0 & 0xffffffu) * 0x9e3779b1u) >> p.vt_shift_b));
+    if (vt_slots_a) ea = vt2(vt_slots_a + 2u * (((x0 & 0xffffu) * 0x9e3779b1u) >> pc.shift_a));
+    if (vt_slots_b && room >= 3) eb = vt2(vt_slots_b + 2u * (((x0 & 0xffffffu) * 0x9e3779b1u) >> pc.shift_b));
     const uint32_t nrec = ea.y + eb.y;
     if (nrec == 0) return; // most candidates end here: no pattern begins with these bytes
-    const uint32_t x1 = room > 4 ? text_window(p, d, entry_sa, i + 4, room - 4) : 0u;
+    const uint32_t x1 = room > 4 ? text_window(d, entry_sa, i + 4, room - 4) : 0u;
+    const uint32_t vt_rec = pc.rec;
     for (uint32_t j = 0; j < nrec; j++) {
-        const uint32_t r = p.vt_rec + 8u * (j < ea.y ? ea.x + j : eb.x + (j - ea.y));
+        const uint32_t r = vt_rec + 8u * (j < ea.y ? ea.x + j : eb.x + (j - ea.y));
         const uint4 a = vt4(r); // pattern bytes 0..3, their mask, bytes 4..7, their mask
         if ((((x0 ^ a.x) & a.y) | ((x1 ^ a.z) & a.w)) != 0) continue;
         const uint2 b = vt2(r + 4); // length, distinct id
@@ -374,14 +404,14 @@ __device__ __forceinline__ void verify_start(const union_params &p, const drain_
         if (m > room) continue;
         bool same = true;
         if (m > 8) {
-            const uint32_t pw0 = p.vt_blob + vt(r + 6);
+            const uint32_t pw0 = dc(DC_BLOB) + vt(r + 6);
             for (uint32_t jj = 8; jj < m && same; jj += 4) { // pattern bytes jj..jj+3 against text bytes i+jj..
                 const uint32_t pw = vt(pw0 + (jj >> 2)), rem = m - jj;
-                const uint32_t diff = text_window(p, d, entry_sa, i + jj, rem) ^ pw;
+                const uint32_t diff = text_window(d, entry_sa, i + jj, rem) ^ pw;
                 same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
             }
         }
-        if (same) count_hit(p, d, b.y);
+        if (same) count_hit(d, b.y);
     }
 }
 
@@ -396,18 +426,21 @@ __device__ __forceinline__ void verify_start(const union_params &p, const drain_
 // event carries its item's parity, and what the resolve step has to know about either item waits in the warp's
 // scratch words, where the warp put it when it took the item: no lane has to look anything up in global memory for
 // it, and the row loop does not keep it in registers.  Positions are relative to the item's row0 (32 bits).
-__device__ __noinline__ void drain_events(const union_params &p, const uint32_t head, const uint32_t n)
+__device__ __noinline__ void drain_events(const uint32_t head, const uint32_t n)
 {
-    const drain_args d = make_drain_args(p);
+    drain_args d;
+    d.q_sa = warp_q_sa();
+    d.scratch_sa = warp_scratch_sa();
+    d.vtab_sa = dc(DC_VTAB_SA);
+    d.counts_sa = dc(DC_COUNTS_SA);
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t lutL = d.lutL, mul1 = p.mul64;
+    const uint32_t lutL = smem_sa() + (lane << 2), mul1 = dc(DC_MUL64);
     uint32_t lt;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     __syncwarp();
     const uint32_t entry_sa = d.q_sa + ((head + lane) & (UN_QCAP - 1)) * UN_Q_BYTES1;
     uint32_t cm = 0, zm = 0, gq = 0, par = 0;
-    uint32_t ks = 0, ke = 0, b_rel = 0, e_rel = 0, row0_lo = 0, row0_hi = 0, carry = 0;
-    float per_byte = 0.f;
+    uint32_t ks = 0, ke = 0, b_rel = 0, e_rel = 0, row0_lo = 0, carry = 0, psize = 0;
     if (lane < n) {
         const uint2 t = lds64v(entry_sa + 40); // group index (relative to row0) | item parity << 31, quarter reports
         par = t.x >> 31;
@@ -415,7 +448,7 @@ __device__ __noinline__ void drain_events(const union_params &p, const uint32_t 
         const uint32_t set_sa = d.scratch_sa + (par << 5); // my item's scratch set
         const uint4 s0 = lds128v(set_sa), s1 = lds128v(set_sa + 16);
         ks = s0.x; ke = s0.y; b_rel = s0.z; e_rel = s0.w;
-        row0_lo = s1.x; row0_hi = s1.y; carry = s1.z; per_byte = __uint_as_float(s1.w);
+        row0_lo = s1.x; carry = s1.z; psize = s1.w;
         // Re-run the filter over the quarters that reported (usually one), one byte per update, this time recording
         // which start positions fired and which bytes are NUL.  Quarter k: bytes 8k..8k+11 -- three bytes of run-in,
         // then the starts 8k..8k+8 report at the bytes 8k+3..8k+11, and so do the NULs among the bytes 8k..8k+8 (the
@@ -467,15 +500,29 @@ __device__ __noinline__ void drain_events(const union_params &p, const uint32_t 
     uint32_t am = 0, bm = 0, nextb = 255; // alive candidates; packet starts inside the group (bit = offset);
                                           // offset of the first packet start at or after the group's end
     if (cm) {
-        // The packet that holds my first candidate: the last k in [ks, ke) with offsets[k] <= p0.  First
-        // guess by interpolation (exact for equal-sized packets), then a binary search in what is left.
-        // Offsets relative to row0 fit 32 bits and need the low words only.
-        const uint32_t *olo = reinterpret_cast<const uint32_t *>(p.offsets);
-        auto orel = [&](uint32_t k) -> uint32_t { return __ldg(olo + 2u * k) - row0_lo; };
+        // The packet that holds my first candidate: the last k in [ks, ke) with offsets[k] <= p0.  When all the item's
+        // packets have the same size (the row loop found out when it took the item) it is a division; otherwise a guess
+        // by interpolation, then a binary search in what is left of the item's slice of `offsets` (relative to row0 they
+        // fit 32 bits and need the low words only).
         const uint32_t p0 = gq + (__ffs(cm) - 1);
-        uint32_t k = ks, k1 = ke;
-        {
-            uint32_t kg = ks + (uint32_t)((float)(p0 - b_rel) * per_byte);
+        const bool uniform = (psize >> 31) != 0;
+        const uint32_t L = psize & 0x7fffffffu;
+        const uint32_t *olo = reinterpret_cast<const uint32_t *>(dc_ptr(DC_OFF_LO));
+        auto orel = [&](uint32_t k) -> uint32_t { return __ldg(olo + 2u * k) - row0_lo; };
+        uint32_t k, ps, pe;
+        if (uniform) {
+            const uint32_t x = p0 - b_rel;
+            uint32_t q = (uint32_t)((float)x * __frcp_rn((float)L)); // x < 2^24 or the quotient is small: off by one at most
+            int32_t r = (int32_t)(x - q * L);
+            if (r < 0) { q--; r += (int32_t)L; }
+            if (r >= (int32_t)L) { q++; r -= (int32_t)L; }
+            k = ks + q;
+            ps = p0 - (uint32_t)r;
+            pe = ps + L;
+        } else {
+            uint32_t k1 = ke;
+            k = ks;
+            uint32_t kg = ks + (uint32_t)((float)(p0 - b_rel) * __uint_as_float(psize));
             kg = kg >= ke ? ke - 1 : kg;
             const uint32_t o0 = orel(kg), o1 = orel(kg + 1);
             if (o0 <= p0) {
@@ -485,12 +532,13 @@ __device__ __noinline__ void drain_events(const union_params &p, const uint32_t 
             } else {
                 k1 = kg;
             }
+            while (k1 - k > 1) {
+                const uint32_t mid = k + (k1 - k) / 2;
+                if (orel(mid) <= p0) k = mid; else k1 = mid;
+            }
+            ps = orel(k);
+            pe = orel(k + 1);
         }
-        while (k1 - k > 1) {
-            const uint32_t mid = k + (k1 - k) / 2;
-            if (orel(mid) <= p0) k = mid; else k1 = mid;
-        }
-        uint32_t ps = orel(k), pe = orel(k + 1);
         bool dead = prev1 > ps; // a NUL in [ps, my bytes): kmp_matcher's strlen() stopped before them
         uint32_t a = ps > gq ? ps - gq : 0u; // the packet [ps, pe) covers my group from offset a on
         for (;;) {
@@ -504,7 +552,7 @@ __device__ __noinline__ void drain_events(const union_params &p, const uint32_t 
             dead = false;
             k++;
             ps = pe;
-            pe = orel(k + 1);
+            pe = uniform ? pe + L : orel(k + 1);
         }
         nextb = pe - gq > 255 ? 255u : pe - gq;
     }
@@ -525,6 +573,12 @@ __device__ __noinline__ void drain_events(const union_params &p, const uint32_t 
     const uint32_t excl = incl - cnt;
     __syncwarp();
     // one alive candidate per lane, whichever event it belongs to
+    probe_consts pc;
+    {
+        const uint4 c0 = lds128(smem_sa() + UN_OFF_MISC + 4u * DC_SLOTS_A);
+        const uint2 c1 = lds64(smem_sa() + UN_OFF_MISC + 4u * DC_ONE);
+        pc.slots_a = c0.x; pc.shift_a = c0.y; pc.slots_b = c0.z; pc.shift_b = c0.w; pc.one = c1.x; pc.rec = c1.y;
+    }
     for (uint32_t t0 = 0; t0 < total; t0 += 32) {
         const uint32_t t = t0 + lane;
         // owner of candidate t: the first lane whose inclusive count exceeds t
@@ -544,8 +598,8 @@ __device__ __noinline__ void drain_events(const union_params &p, const uint32_t 
             const uint32_t onext = lds32v(owner_sa + 36), obm = lds32v(owner_sa + 44);
             const uint32_t above = obm & ~((2u << i) - 1u); // packet starts after byte i
             const uint32_t room = (above ? (uint32_t)__ffs(above) - 1u : onext) - i;
-            if (p.vtab_in_smem) verify_start<true>(p, d, owner_sa, i, room);
-            else verify_start<false>(p, d, owner_sa, i, room);
+            if (d.vtab_sa) verify_start<true>(d, pc, owner_sa, i, room);
+            else verify_start<false>(d, pc, owner_sa, i, room);
         }
     }
     __syncwarp();
@@ -586,18 +640,37 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         for (uint32_t i = threadIdx.x; i < p.vtab_words; i += UN_THREADS) s_vtab[i] = p.vtab[i];
     for (uint32_t i = threadIdx.x; i < UN_SCRATCH_BYTES / 4; i += UN_THREADS)
         reinterpret_cast<uint32_t *>(smem + UN_OFF_SCRATCH)[i] = 0; // item parity, pending flag, carries
+    if (threadIdx.x == 0) {
+        const uint64_t text0 = reinterpret_cast<uint64_t>(p.bytes) - p.abs_base, off = reinterpret_cast<uint64_t>(p.offsets);
+        const uint64_t vt = reinterpret_cast<uint64_t>(p.vtab), cn = reinterpret_cast<uint64_t>(p.uniq_counts);
+        s_misc[DC_TEXT_LO] = (uint32_t)text0; s_misc[DC_TEXT_HI] = (uint32_t)(text0 >> 32);
+        s_misc[DC_OFF_LO] = (uint32_t)off; s_misc[DC_OFF_HI] = (uint32_t)(off >> 32);
+        s_misc[DC_VTAB_LO] = (uint32_t)vt; s_misc[DC_VTAB_HI] = (uint32_t)(vt >> 32);
+        s_misc[DC_CNT_LO] = (uint32_t)cn; s_misc[DC_CNT_HI] = (uint32_t)(cn >> 32);
+        s_misc[DC_SLOTS_A] = p.vt_slots_a; s_misc[DC_SHIFT_A] = p.vt_shift_a;
+        s_misc[DC_SLOTS_B] = p.vt_slots_b; s_misc[DC_SHIFT_B] = p.vt_shift_b;
+        s_misc[DC_ONE] = p.vt_one; s_misc[DC_REC] = p.vt_rec; s_misc[DC_BLOB] = p.vt_blob;
+        s_misc[DC_MUL64] = p.mul64;
+        s_misc[DC_VTAB_SA] = p.vtab_in_smem ? saddr_of(s_vtab) : 0u;
+        s_misc[DC_COUNTS_SA] = p.counts_in_smem ? saddr_of(s_counts) : 0u;
+    }
     const uint32_t lane = threadIdx.x & 31;
     __syncthreads();
 
-        const uint32_t lutL = saddr_of(lut) + (lane << 2), lutG = lutL + UN_LUT_BYTES;
+        static_assert(UN_LUT_BYTES == 32768, "lds32_g's immediate offset");
+    const uint32_t lutL = saddr_of(lut) + (lane << 2);
     const uint32_t mul2 = p.mul4096;
-    uint32_t qn = 0, qw = 0; // pending events and the ring slot the next one goes to (the oldest sits at qw - qn)
+    const uint32_t q_sa = warp_q_sa();
+    // the event ring's state in one register: pending events << 16 | ring slot the next one goes to (mod 2^16; the
+    // oldest pending event sits at slot (next - pending) mod UN_QCAP)
+    uint32_t qs = 0;
+    auto pending = [&]() -> uint32_t { return qs >> 16; };
 
-    // resolve the oldest min(qn, 32) events
+    // resolve the oldest min(pending, 32) events
     auto resolve_oldest = [&]() {
-        const uint32_t n = qn < UN_QDRAIN ? qn : UN_QDRAIN;
-        drain_events(p, (qw - qn) & (UN_QCAP - 1), n);
-        qn -= n;
+        const uint32_t qn = qs >> 16, n = qn < UN_QDRAIN ? qn : UN_QDRAIN;
+        drain_events((qs - qn) & (UN_QCAP - 1), n);
+        qs -= n << 16;
     };
 
     for (;;) {
@@ -619,42 +692,53 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         // which case they are now.
         const uint2 st = lds64v(warp_scratch_sa() + SC_STATE); // parity of the previous item, pending flag
         const uint32_t par = st.x ^ 1u;
-        if (qn && st.y)
-            while (qn) resolve_oldest();
+        if (pending() && st.y)
+            while (pending()) resolve_oldest();
         __syncwarp();
         const uint64_t row0 = b_abs & ~127ull; // absolute position of the item's first row
         const uint32_t b_rel = (uint32_t)(b_abs - row0), e_rel = (uint32_t)(e_abs - row0);
+        // do all the item's packets have the same size?  (fixed-size records: the packet lookup becomes a division)
+        uint32_t psize;
+        {
+            const uint64_t L = uni(p.offsets[ks + 1]) - b_abs;
+            bool same = L != 0 && L * (ke - ks) == e_abs - b_abs;
+            for (uint32_t j = lane + 1; same && j < ke - ks; j += 32) same = p.offsets[ks + j] == b_abs + j * L;
+            same = __all_sync(FULL, same);
+            psize = same ? 0x80000000u | (uint32_t)L : __float_as_uint((float)(ke - ks) / (float)(e_rel - b_rel));
+        }
         if (lane == 0) {
             const uint32_t set_sa = warp_scratch_sa() + (par << 5);
             sts128v(set_sa, ks, ke, b_rel, e_rel);
-            sts128v(set_sa + 16, (uint32_t)row0, (uint32_t)(row0 >> 32), 0u, __float_as_uint((float)(ke - ks) / (float)(e_rel - b_rel)));
-            sts64v(warp_scratch_sa() + SC_STATE, par, qn ? 1u : 0u);
+            sts128v(set_sa + 16, (uint32_t)row0, (uint32_t)(row0 >> 32), 0u, psize);
+            sts64v(warp_scratch_sa() + SC_STATE, par, pending() ? 1u : 0u);
         }
-        const uint8_t *textl = p.bytes + (row0 - p.abs_base) + lane * UN_GRP; // my 32 bytes of the item's first row
+        // The loop state of a lane, kept small (the filter needs the registers):
+        //   src  = its 32 bytes of the row being scanned,
+        //   left = bytes from there to the end of what the item lets it load (<= 0: nothing of this row is its to load),
+        //   gcur = its group's index relative to row0 (32-byte units) | the item's parity << 31.
+        const uint8_t *src = p.bytes + (row0 - p.abs_base) + lane * UN_GRP;
         const uint32_t load_end = (e_rel + 31u) & ~31u; // readable: the batch up to its end rounded up to 32 (kmpb200.h)
-        // my group of the row at item offset `off` is loaded when off < lim; lane 31's lookahead when off + 32 < lim
-        const uint32_t lim = load_end > lane * UN_GRP ? load_end - lane * UN_GRP : 0u;
-        // my group's index in row 0 (relative to row0, in 32-byte units) and the item's parity
-        const uint32_t g32 = lane | par << 31;
+        int32_t left = (int32_t)load_end - (int32_t)(lane * UN_GRP);
+        uint32_t gcur = lane | par << 31;
 
-        // The row at item offset `off`, global -> registers: every lane its own 32 bytes with one 256-bit load, lane 31
-        // also the 4 bytes after the row (its lookahead; the other lanes find theirs in the next lane's registers).
-        // Rows past the item's end and the lanes past load_end in its last row load nothing and keep what they held:
-        // whatever they report from it is cut to the item's byte range by the resolve step.  The L2 prefetch of the
-        // row UN_PF rows further on rides on the same address.
-        auto load_row = [&](const uint32_t off, row_regs &b) {
-            const uint8_t *src = add_wide(textl, off); // one multiply-add on the FMA pipe instead of two ALU adds
-            ldg256_if(off < lim, b, src);
-            ldg32_if(lane == 31 && off + UN_GRP < lim, b.la, src + UN_GRP);
-            if (UN_PF) prefetch_l2_if(off + UN_PF * UN_ROW < lim, src + UN_PF * UN_ROW);
+        // The row `ahead` rows after the one being scanned, global -> registers: every lane its own 32 bytes with one
+        // 256-bit load.  Rows past the item's end and the lanes past load_end in its last row load nothing and keep
+        // what they held: whatever they report from it is cut to the item's byte range by the resolve step.  The L2
+        // prefetch of the row UN_PF rows further on rides on the same address.
+        auto load_row = [&](const uint32_t ahead, row_regs &b) {
+            const int32_t l = left - (int32_t)(ahead * UN_ROW);
+            const uint8_t *s = src + ahead * UN_ROW;
+            ldg256_if(l > 0, b, s);
+            if (UN_PF) prefetch_l2_if(l > (int32_t)(UN_PF * UN_ROW), s + UN_PF * UN_ROW);
         };
 
         // one row: filter its bytes, append the events, refill the buffer with the row UN_NBUF ahead, and resolve
         // 32 events once the list holds that many
-        auto scan_row = [&](const uint32_t off, row_regs &b) {
-            // the 4 bytes after my group: the next lane's first word, for lane 31 the first of the next row
-            const uint32_t la_next = __shfl_down_sync(FULL, b.w[0], 1);
-            const uint32_t la = lane == 31 ? b.la : la_next;
+        auto scan_row = [&](row_regs &b) {
+            // the 4 bytes after my group: the next lane's first word; for lane 31 the first word of the next row, asked
+            // for now (the row's own load is already on its way, so it comes from L2 or rides on that fill) and used last
+            const uint32_t la31 = ldg32_if(lane == 31 && left > (int32_t)UN_GRP, src + UN_GRP);
+            uint32_t la = __shfl_down_sync(FULL, b.w[0], 1);
 
             // ---- shift-and filter over 36 bytes, two per update ---------------------------------------
             // Update j takes bytes 2j, 2j+1 and reports what starts at 2j-3 (bits 24..29) and 2j-2 (bits 18..23): the
@@ -676,6 +760,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             acc2 |= SA2(b.w[6], 2);                 // 23, 24
             acc3 = SA2(b.w[7], 0);                  // 25, 26
             acc3 |= SA2(b.w[7], 2);
+            la = lane == 31 ? la31 : la;
             acc3 |= SA2(la, 0);                     // 29, 30
             SA2(la, 2);                             // 31 | 32: the next lane's
             acc3 |= S & F6_HI;
@@ -700,20 +785,18 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                 if (tp != 0) {
                     uint32_t lt;
                     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
-                    const uint32_t e = warp_q_sa() + ((qw + __popc(mp & lt)) & (UN_QCAP - 1)) * UN_Q_BYTES1;
+                    const uint32_t e = q_sa + ((qs + __popc(mp & lt)) & (UN_QCAP - 1)) * UN_Q_BYTES1;
                     sts128v(e, b.w[0], b.w[1], b.w[2], b.w[3]);
                     sts128v(e + 16, b.w[4], b.w[5], b.w[6], b.w[7]);
-                    sts128v(e + 32, la, 0u, g32 + (off >> 5), tp);
+                    sts128v(e + 32, la, 0u, gcur, tp);
                 }
-                const uint32_t np = __popc(mp);
-                qn += np;
-                qw += np;
+                qs += __popc(mp) * 0x10001u;
             }
             // the buffer is free: the row UN_NBUF ahead goes into it
-            load_row(off + UN_NBUF * UN_ROW, b);
+            load_row(UN_NBUF, b);
             // with the loads on their way: resolve 32 events if there are that many (no event of the item before this
             // one is left afterwards: there were fewer than 32 of them when this item was taken)
-            if (qn >= UN_QDRAIN) {
+            if (qs >= (UN_QDRAIN << 16)) {
                 resolve_oldest();
                 if (lane == 0) sts32v(warp_scratch_sa() + SC_STATE + 4, 0u);
             }
@@ -721,38 +804,44 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
 
         // the first UN_PF rows' lines: 128 bytes per lane and step
         if (UN_PF)
-            for (uint32_t x = lane * 128u; x < UN_PF * UN_ROW; x += 4096u) prefetch_l2_if(x < load_end, textl - lane * UN_GRP + x);
+            for (uint32_t x = lane * 128u; x < UN_PF * UN_ROW; x += 4096u) prefetch_l2_if(x < load_end, src - lane * UN_GRP + x);
         // UN_NBUF rows per trip: the buffers are compile-time registers, no moves between them
         row_regs b0 = {}, b1 = {};
         load_row(0, b0);
-        load_row(UN_ROW, b1);
+        load_row(1, b1);
 #if KMPB_UN_NBUF >= 3
         row_regs b2 = {};
-        load_row(2 * UN_ROW, b2);
+        load_row(2, b2);
 #endif
 #if KMPB_UN_NBUF >= 4
         row_regs b3 = {};
-        load_row(3 * UN_ROW, b3);
+        load_row(3, b3);
 #endif
-        uint32_t off = 0;
+        // next row; the item is through when lane 0 has nothing left (its rows start at multiples of 32)
+        auto advance = [&]() -> bool {
+            src += UN_ROW;
+            left -= (int32_t)UN_ROW;
+            gcur += UN_ROW / UN_GRP;
+            return left + (int32_t)(lane * UN_GRP) <= 0;
+        };
 #pragma unroll 1
         for (;;) {
-            scan_row(off, b0);
-            if ((off += UN_ROW) >= e_rel) break;
-            scan_row(off, b1);
-            if ((off += UN_ROW) >= e_rel) break;
+            scan_row(b0);
+            if (advance()) break;
+            scan_row(b1);
+            if (advance()) break;
 #if KMPB_UN_NBUF >= 3
-            scan_row(off, b2);
-            if ((off += UN_ROW) >= e_rel) break;
+            scan_row(b2);
+            if (advance()) break;
 #endif
 #if KMPB_UN_NBUF >= 4
-            scan_row(off, b3);
-            if ((off += UN_ROW) >= e_rel) break;
+            scan_row(b3);
+            if (advance()) break;
 #endif
         }
     }
     // leftovers
-    while (qn) resolve_oldest();
+    while (pending()) resolve_oldest();
 
     __syncthreads();
     if (p.counts_in_smem)
@@ -766,9 +855,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     if (p.n_out) {
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_misc[0] = atomicAdd(&p.work[2], 1u) == gridDim.x - 1 ? 1u : 0u;
+        if (threadIdx.x == 0) s_misc[DC_LAST] = atomicAdd(&p.work[2], 1u) == gridDim.x - 1 ? 1u : 0u;
         __syncthreads();
-        if (s_misc[0]) {
+        if (s_misc[DC_LAST]) {
             __threadfence();
             for (uint32_t i = threadIdx.x; i < p.n_pat; i += UN_THREADS) {
                 const unsigned long long v = __ldcg(p.uniq_counts + p.pat_to_uniq[i]);
