@@ -283,6 +283,27 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_bench_reference_arm_loads_no_product_code():
+    """The reference arm must not run anything of the product: its sample comes from bench.py's numpy twin of the
+    generator, which has to produce the very bytes of csrc/cuda/synth.cu, and libkmpb200.so is never mapped."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    pats = kmp.load_patterns(os.path.join(DATA, "strings.txt"))
+    assert bench.load_patterns_py(os.path.join(DATA, "strings.txt")) == pats
+    for first, count, L in ((0, 700, 1400), (123457, 300, 1400), (5, 200, 64), (0, 40, 9000)):
+        want, want_off = kmp.Synth(seed=bench.SEED, payload_len=L, plants=2, plant_patterns=pats).fill_host(first, count)
+        got, got_off = bench.synth_stream(bench.SEED, first, count, L, 2, pats)
+        assert np.array_equal(got, want) and np.array_equal(got_off, want_off)
+    code = ("import sys; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0','--ref-packets','600'];"
+            "import runpy; runpy.run_path(%r, run_name='__main__');"
+            "maps=open('/proc/self/maps').read(); sys.exit(3 if 'libkmpb200' in maps else 0)" % os.path.join(ROOT, "bench.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr[-1500:])
+
+
 def test_host_side_is_sanitizer_clean(tmp_path):
     """The C host side (pattern loader, savefile reader, extractors, CSR packer, streamed packer, table builder,
     report) under AddressSanitizer + UndefinedBehaviorSanitizer over every bundled savefile and over damaged ones
