@@ -69,6 +69,9 @@ const char *kmpb_version(void);
 const char *kmpb_last_error(void);
 /* number of usable (compute capability 10.x) CUDA devices; 0 when there is none */
 int kmpb_device_count(void);
+/* CUDA ordinal of the index-th usable device (0 <= index < kmpb_device_count()), -1 beyond: what kmpb_create wants when
+ * a box also holds GPUs this library has no code for.  The MPI variant's rank -> host mapping (mpi_dumping.c:29-31). */
+int kmpb_device_ordinal(int index);
 
 /* ---- context ------------------------------------------------------------------------------ */
 /* Replaces nothing in the reference (it has no state); owns the device buffers, streams, tables.
@@ -118,12 +121,16 @@ int kmpb_count_device_span(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t
 /* Same, with the reduce across GPUs inside the match kernel: the counts are added to n_vectors (1..8)
  * count vectors of uint64[n_pat] -- this GPU's own and those of its peers, mapped into this process
  * over NVLink (CUDA IPC / symmetric memory) -- by system-scope atomics issued by the kernel's last
- * block.  Replaces the local merge (openmp_data.c:169-173) plus MPI_Reduce(SUM) (mpi_dumping.c:202)
+ * block (union engine) or by the count expansion that follows the match kernel (per-pattern engine).  Replaces the local merge (openmp_data.c:169-173) plus MPI_Reduce(SUM) (mpi_dumping.c:202)
  * for device-resident callers: when every rank has passed its own batch, every vector holds the
  * total.  The caller orders "all ranks have finished" (a barrier) before reading a vector. */
 int kmpb_count_device_span_peers(kmpb_ctx *ctx, const uint8_t *d_bytes, const uint64_t *d_offsets,
                                  uint64_t n_packets, uint64_t first_byte, uint64_t end_byte,
                                  uint64_t *const *d_counts_all, uint32_t n_vectors, void *stream);
+/* The device forms never wait, so they cannot report what only the device knows: a packet of 2 GiB or more (outside
+ * the documented limits; its work item is skipped).  This call waits for the context's device and returns KMPB_ELIMIT
+ * if any device-form call since the last check met one (the host forms check by themselves). */
+int kmpb_check_device_errors(kmpb_ctx *ctx);
 /* Device copy of the per-pattern counts of the last kmpb_count_host call (uint64[n_pat] on the
  * context's GPU), for callers that combine several GPUs with a collective (mpi_dumping.c:202). */
 uint64_t *kmpb_device_counts(kmpb_ctx *ctx);

@@ -39,6 +39,8 @@ SIGNATURES = {
     "kmpb_version": (ctypes.c_char_p, []),
     "kmpb_last_error": (ctypes.c_char_p, []),
     "kmpb_device_count": (ctypes.c_int, []),
+    "kmpb_device_ordinal": (ctypes.c_int, [ctypes.c_int]),
+    "kmpb_check_device_errors": (ctypes.c_int, [ctypes.c_void_p]),
     "kmpb_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
     "kmpb_destroy": (None, [ctypes.c_void_p]),
     "kmpb_set_engine": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -9,7 +9,21 @@
 
 #include "kmpb_device.cuh"
 
+// a CUDA call inside a chunk loop: on failure nothing of the call stays in flight
+#define KMPB_CUDA_Q(ctx, call)                                                                   \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            quiesce(ctx);                                                                        \
+            return kmpb_fail(KMPB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                             __FILE__, __LINE__);                                                \
+        }                                                                                        \
+    } while (0)
+
 namespace {
+
+void quiesce(kmpb_ctx *ctx);
+int device_flags(kmpb_ctx *ctx, int n_slots);
 
 int use_device(const kmpb_ctx *ctx)
 {
@@ -24,7 +38,9 @@ bool device_is_sm100(int device)
     return prop.major == 10; // the library carries sm_100a code only
 }
 
-// counts[i] (+)= sum over slots of uniq_counts[slot][pat_to_uniq[i]]
+// counts[i] (+)= sum over slots of uniq_counts[slot][pat_to_uniq[i]].  accumulate: 0 = overwrite, 1 = add (the vector
+// is this caller's alone), 2 = add with system-scope atomics (the vector may be a peer GPU's, mapped over NVLink, and
+// other ranks may be adding to it at the same time)
 __global__ void kmpb_expand_counts_kernel(const unsigned long long *__restrict__ uniq_counts, uint32_t n_uniq,
                                           int n_slots, const uint32_t *__restrict__ pat_to_uniq, uint32_t n_pat,
                                           unsigned long long *__restrict__ counts, int accumulate)
@@ -32,9 +48,13 @@ __global__ void kmpb_expand_counts_kernel(const unsigned long long *__restrict__
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pat) return;
     const uint32_t u = pat_to_uniq[i];
-    unsigned long long v = accumulate ? counts[i] : 0ull;
+    unsigned long long v = 0ull;
     for (int s = 0; s < n_slots; s++) v += uniq_counts[(size_t)s * n_uniq + u];
-    counts[i] = v;
+    if (accumulate == 2) {
+        if (v) atomicAdd_system(counts + i, v);
+    } else {
+        counts[i] = (accumulate ? counts[i] : 0ull) + v;
+    }
 }
 
 int run_engine(kmpb_ctx *ctx, const kmpb_batch &b, int slot, cudaStream_t stream)
@@ -109,14 +129,43 @@ int finish_chunked(kmpb_ctx *ctx, int n_slots, uint64_t *counts_out)
     ctx->last_ms[0] = ms;
     ctx->last_ms[1] = 0;
     // device-side error flags of the union engine (oversized packets)
-    if (ctx->engine != KMPB_ENGINE_PERPAT && ctx->d_work) {
-        uint32_t work[KMPB_COPY_STREAMS * 4];
-        KMPB_CUDA(cudaMemcpy(work, ctx->d_work, sizeof work, cudaMemcpyDeviceToHost));
-        for (int s = 0; s < n_slots; s++)
-            if (work[s * 4 + 1])
-                return kmpb_fail(KMPB_ELIMIT, work[s * 4 + 1] & 2u ? "unexpected shared-memory window layout on this device"
-                                                                   : "a packet of 2 GiB or more is not supported");
-    }
+    if (ctx->engine != KMPB_ENGINE_PERPAT) return device_flags(ctx, n_slots);
+    return KMPB_OK;
+}
+
+int init_context(kmpb_ctx *ctx)
+{
+    const int device = ctx->device;
+    KMPB_CUDA(cudaSetDevice(device));
+    int v = 0;
+    KMPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+    ctx->sm_count = v;
+    KMPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    ctx->smem_optin = (size_t)v;
+    KMPB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto &s : ctx->copy_stream) KMPB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) KMPB_CUDA(cudaEventCreate(&ev));
+    for (auto &ev : ctx->ev_kernel) KMPB_CUDA(cudaEventCreate(&ev));
+    return KMPB_OK;
+}
+
+// every copy stream idle again: an error return must not leave copies or kernels of the call in flight
+void quiesce(kmpb_ctx *ctx)
+{
+    for (auto &s : ctx->copy_stream)
+        if (s) cudaStreamSynchronize(s);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
+}
+
+// the union engine's device-side error flags of scratch slots [0, n_slots)
+int device_flags(kmpb_ctx *ctx, int n_slots)
+{
+    if (ctx->d_work == nullptr) return KMPB_OK;
+    uint32_t work[KMPB_COPY_STREAMS * 4];
+    KMPB_CUDA(cudaMemcpy(work, ctx->d_work, sizeof work, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < n_slots; s++)
+        if (work[s * 4 + 1]) return kmpb_fail(KMPB_ELIMIT, "a packet of 2 GiB or more is not supported (its work item was skipped)");
     return KMPB_OK;
 }
 
@@ -130,6 +179,24 @@ int kmpb_device_count(void)
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     for (int d = 0; d < n; d++) usable += device_is_sm100(d) ? 1 : 0;
     return usable;
+}
+
+int kmpb_device_ordinal(int index)
+{
+    int n = 0;
+    if (index < 0 || cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (int d = 0; d < n; d++)
+        if (device_is_sm100(d) && index-- == 0) return d;
+    return -1;
+}
+
+int kmpb_check_device_errors(kmpb_ctx *ctx)
+{
+    if (ctx == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL context");
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    KMPB_CUDA(cudaDeviceSynchronize());
+    return device_flags(ctx, KMPB_COPY_STREAMS);
 }
 
 int kmpb_create(kmpb_ctx **out, int device)
@@ -149,16 +216,11 @@ int kmpb_create(kmpb_ctx **out, int device)
     kmpb_ctx *ctx = new (std::nothrow) kmpb_ctx();
     if (ctx == nullptr) return kmpb_fail(KMPB_ENOMEM, "out of memory");
     ctx->device = device;
-    KMPB_CUDA(cudaSetDevice(device));
-    int v = 0;
-    KMPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
-    ctx->sm_count = v;
-    KMPB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    ctx->smem_optin = (size_t)v;
-    KMPB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    for (auto &s : ctx->copy_stream) KMPB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    for (auto &ev : ctx->ev) KMPB_CUDA(cudaEventCreate(&ev));
-    for (auto &ev : ctx->ev_kernel) KMPB_CUDA(cudaEventCreate(&ev));
+    const int rc = init_context(ctx);
+    if (rc != KMPB_OK) { // whatever was created so far goes away again; *out stays NULL
+        kmpb_destroy(ctx);
+        return rc;
+    }
     *out = ctx;
     return KMPB_OK;
 }
@@ -290,7 +352,7 @@ static int count_device_span_into(kmpb_ctx *ctx, const uint8_t *d_bytes, const u
     for (uint32_t r = 0; r < n_vectors; r++) {
         kmpb_expand_counts_kernel<<<(ctx->host.n_pat + 255) / 256, 256, 0, stream>>>(
             (const unsigned long long *)ctx->d_uniq_counts, nu, 1, ctx->dev.pat_to_uniq, ctx->host.n_pat,
-            (unsigned long long *)d_counts[r], 1);
+            (unsigned long long *)d_counts[r], n_vectors > 1 ? 2 : 1);
         ctx->launches++;
     }
     KMPB_CUDA(cudaGetLastError());
@@ -341,8 +403,14 @@ int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets
     memset(counts_out, 0, (size_t)n_pat * sizeof(uint64_t));
     if (n_packets == 0) return KMPB_OK;
     if (bytes == nullptr || offsets == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL batch pointer");
-    for (uint64_t k = 0; k < n_packets; k += std::max<uint64_t>(1, n_packets / 64))
-        if (offsets[k + 1] < offsets[k]) return kmpb_fail(KMPB_EINVAL, "offsets decrease at packet %llu", (unsigned long long)k);
+    {   // every offset, not a sample: a decreasing pair anywhere would size a copy wrongly (one pass over 8 bytes per
+        // packet, all host threads; nothing next to copying the packets themselves)
+        int64_t bad = -1;
+#pragma omp parallel for schedule(static) reduction(max : bad)
+        for (int64_t k = 0; k < (int64_t)n_packets; k++)
+            if (offsets[k + 1] < offsets[k] && k > bad) bad = k;
+        if (bad >= 0) return kmpb_fail(KMPB_EINVAL, "offsets decrease at packet %lld", (long long)bad);
+    }
     int rc = use_device(ctx);
     if (rc) return rc;
 
@@ -379,10 +447,10 @@ int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets
         cudaStream_t s = ctx->copy_stream[slot];
         const uint64_t k0 = plan[c].k0, k1 = plan[c].k1;
         const uint64_t base = offsets[k0] & ~511ull;
-        KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_bytes[slot], bytes + base, offsets[k1] - base, cudaMemcpyHostToDevice, s));
-        KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_off[slot], offsets + k0, (k1 - k0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        KMPB_CUDA_Q(ctx, cudaMemcpyAsync(ctx->d_stage_bytes[slot], bytes + base, offsets[k1] - base, cudaMemcpyHostToDevice, s));
+        KMPB_CUDA_Q(ctx, cudaMemcpyAsync(ctx->d_stage_off[slot], offsets + k0, (k1 - k0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         kmpb_batch b{ctx->d_stage_bytes[slot], base, ctx->d_stage_off[slot], k1 - k0, offsets[k0], offsets[k1]};
-        if ((rc = run_engine(ctx, b, slot, s))) return rc;
+        if ((rc = run_engine(ctx, b, slot, s))) { quiesce(ctx); return rc; }
     }
     return finish_chunked(ctx, n_slots, counts_out);
 }
@@ -437,16 +505,16 @@ int kmpb_count_pcap(kmpb_ctx *ctx, const kmpb_pcap *pc, uint64_t first, uint64_t
         uint64_t nbytes = 0;
         const uint64_t k1 = kmpb_pcap_chunk_end(pc, k0, last, chunk_bytes, max_pkts, &nbytes);
         const double t0 = now();
-        if (c >= KMPB_COPY_STREAMS) KMPB_CUDA(cudaEventSynchronize(ctx->ev_h2d[slot])); // the slot's last copy has left it
+        if (c >= KMPB_COPY_STREAMS) KMPB_CUDA_Q(ctx, cudaEventSynchronize(ctx->ev_h2d[slot])); // the slot's last copy has left it
         const double t1 = now();
         kmpb_pcap_pack(pc, k0, k1 - k0, ctx->h_stage_bytes[slot], ctx->h_stage_off[slot]);
         memset(ctx->h_stage_bytes[slot] + nbytes, 0, 64);
         const double t2 = now();
-        KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_bytes[slot], ctx->h_stage_bytes[slot], nbytes + 64, cudaMemcpyHostToDevice, s));
-        KMPB_CUDA(cudaMemcpyAsync(ctx->d_stage_off[slot], ctx->h_stage_off[slot], (k1 - k0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-        KMPB_CUDA(cudaEventRecord(ctx->ev_h2d[slot], s));
+        KMPB_CUDA_Q(ctx, cudaMemcpyAsync(ctx->d_stage_bytes[slot], ctx->h_stage_bytes[slot], nbytes + 64, cudaMemcpyHostToDevice, s));
+        KMPB_CUDA_Q(ctx, cudaMemcpyAsync(ctx->d_stage_off[slot], ctx->h_stage_off[slot], (k1 - k0 + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        KMPB_CUDA_Q(ctx, cudaEventRecord(ctx->ev_h2d[slot], s));
         kmpb_batch b{ctx->d_stage_bytes[slot], 0, ctx->d_stage_off[slot], k1 - k0, 0, nbytes};
-        if ((rc = run_engine(ctx, b, slot, s))) return rc;
+        if ((rc = run_engine(ctx, b, slot, s))) { quiesce(ctx); return rc; }
         k0 = k1;
         t_wait += t1 - t0;
         t_pack += t2 - t1;

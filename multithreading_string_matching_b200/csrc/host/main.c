@@ -40,7 +40,8 @@ typedef struct {
 } ingest_gate;
 
 typedef struct {
-    int device;
+    int device; /* CUDA ordinal */
+    int rank;   /* which share of the packets */
     const kmpb_patterns *pats;
     ingest_gate *gate;
     uint64_t *counts;
@@ -65,7 +66,7 @@ static void *run_shard(void *arg)
     pthread_mutex_unlock(&job->gate->lock);
     if (job->rc == 0 && pc != NULL) {
         uint64_t first, count;
-        kmpb_shard_range(kmpb_pcap_packets(pc), (uint32_t)job->gate->n_gpus, (uint32_t)job->device, &first, &count);
+        kmpb_shard_range(kmpb_pcap_packets(pc), (uint32_t)job->gate->n_gpus, (uint32_t)job->rank, &first, &count);
         job->rc = kmpb_count_pcap(ctx, pc, first, count, job->counts);
         if (job->rc != 0) snprintf(job->err, sizeof job->err, "%s", kmpb_last_error());
     }
@@ -126,7 +127,8 @@ int main(int argc, char **argv)
     shard_job *jobs = calloc((size_t)n_gpus, sizeof *jobs);
     pthread_t *threads = calloc((size_t)n_gpus, sizeof *threads);
     for (int g = 0; g < n_gpus; g++) {
-        jobs[g].device = g;
+        jobs[g].device = kmpb_device_ordinal(g); /* the g-th usable GPU, whatever else the box holds */
+        jobs[g].rank = g;
         jobs[g].pats = &pats;
         jobs[g].gate = &gate;
         jobs[g].start = start;

@@ -394,15 +394,18 @@ def test_sparse_events_over_many_work_items(matchers, oracle):
     assert m.count_host(hdata, hoff) == oracle.count_csr(hdata, hoff, pats)
 
 
-def test_fused_reduce_into_several_vectors(matchers, oracle, strings):
-    """kmpb_count_device_span_peers: the kernel's last block adds the counts to every vector it is given
-    (on a multi-GPU box the other vectors are peers' memory; here they are local)."""
+@pytest.mark.parametrize("engine", ["union", "perpat"])
+def test_fused_reduce_into_several_vectors(matchers, oracle, strings, engine):
+    """kmpb_count_device_span_peers: the counts are added to every vector it is given -- by the union kernel's last
+    block, or (per-pattern engine) by the count expansion behind the match kernel, with system-scope atomics in either
+    case (on a multi-GPU box the other vectors are peers' memory; here they are local).  bench.py checks the same
+    across real GPUs at N > 1 (strong.counts_match_unsplit_stream)."""
     import torch
 
     synth = kmp.Synth(seed=5, payload_len=700, plants=2, plant_patterns=strings)
     data, off = synth.fill_host(0, 9000)
     want = oracle.count_csr(data, off, strings)
-    m = matchers["union"]
+    m = matchers[engine]
     m.set_patterns(strings)
     d_bytes = torch.zeros(len(data) + 4096, dtype=torch.uint8, device="cuda:0")
     d_bytes[: len(data)] = torch.from_numpy(np.ascontiguousarray(data)).cuda()
@@ -415,6 +418,7 @@ def test_fused_reduce_into_several_vectors(matchers, oracle, strings):
     assert vecs[0].cpu().tolist() == [2 * w for w in want]
     assert vecs[1].cpu().tolist() == [2 * w for w in want]
     assert vecs[2].cpu().tolist() == [2 * w + 7 for w in want]
+    kmp._lib.check(kmp._lib.lib().kmpb_check_device_errors(m.handle))  # nothing outside the limits was met
 
 
 def test_mixed_length_stream_host_path(matchers, oracle, strings):
