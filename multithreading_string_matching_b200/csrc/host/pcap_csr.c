@@ -2,7 +2,8 @@
  *
  * The reference lets libpcap frame the records (pcap_open_offline serial.c:91, pcap_next_ex :115),
  * copies every frame, extracts its payload and stores one malloc'd buffer per payload.  Here the
- * savefile is mapped, the records are framed and their payloads located in one sequential pass, and
+ * savefile is mapped (its pages faulted in by all host threads), the records are framed and their payloads
+ * located in one sequential pass, and
  * the accepted payloads are then packed back to back by all host threads (OpenMP, like the
  * reference's own extraction loop at openmp_data.c:128-147) into ONE flat buffer plus an offsets
  * array -- the CSR batch the device consumes -- in pinned memory so the H2D copies can run
@@ -209,6 +210,16 @@ int kmpb_pcap_open(const char *path, int proto, kmpb_pcap **out)
     close(fd);
     if (file == MAP_FAILED) return kmpb_fail(KMPB_EIO, "%s: mmap: %s", path, strerror(errno));
     madvise((void *)file, size, MADV_WILLNEED);
+    /* The framing pass below is sequential (record n+1 starts where record n's header says) and touches every page of
+     * the mapping once; what it would spend is mostly the page faults (10 GB in tmpfs: 0.8 s of its 0.85 s).  Faults
+     * scale with threads, the walk does not: all host threads touch the pages first. */
+    if (size >= ((size_t)64 << 20)) {
+        const size_t page = 4096, n_pages = (size + page - 1) / page;
+        unsigned long touched = 0;
+#pragma omp parallel for schedule(static) reduction(+ : touched)
+        for (size_t i = 0; i < n_pages; i++) touched += ((const volatile uint8_t *)file)[i * page];
+        (void)touched;
+    }
 
     uint32_t magic;
     memcpy(&magic, file, 4);
