@@ -2,22 +2,24 @@
  *
  * The reference keeps one KMP failure table per pattern (kmp_prefix, serial.c:217-238) and walks
  * every payload once per pattern (serial.c:153-155).  Walking the payload P times cannot come near
- * the HBM roofline, so the union engine merges the P KMP automata into one DFA over the trie of all
- * pattern prefixes: state = longest suffix of the text read so far that is a prefix of some pattern
- * -- for a single pattern this is exactly the automaton kmp_matcher steps through (j, with the drop
- * to prefix[j-1] on mismatch or after a hit, serial.c:203-211).  A state reports every pattern that
- * is a suffix of it, which is what makes the per-pattern counts independent and overlapping.
+ * the HBM roofline, so the union engine reads it once: a 4-byte-deep shift-and prefilter over 5 buckets
+ * of patterns (+ a NUL detector) finds the few positions where some pattern can start at all
+ * (kmpb_filter6_build), and start-anchored probe tables name the patterns that really do
+ * (build_verify_tables).  Counting every occurrence once at its start gives the numbers P independent
+ * kmp_matcher calls give (overlapping occurrences are separate occurrences either way).
  *
- * On top of it sits a 4-byte-deep shift-and prefilter over 7 buckets of patterns (+1 bucket that
- * detects NUL bytes): the device looks every payload byte up once in `filter` and only walks the DFA
- * around the rare positions where some bucket's first bytes all agree.
+ * For the table tests only (kmpb_tables_build_ex with_dfa): the P KMP automata merged into one DFA over
+ * the trie of all pattern prefixes -- state = longest suffix of the text read so far that is a prefix of
+ * some pattern; for a single pattern exactly the automaton kmp_matcher steps through (j, with the drop
+ * to prefix[j-1] on mismatch or after a hit, serial.c:203-211).  tests/c/test_tables.c checks the filter
+ * and the probe tables against it and against a naive counter.
  */
 #include <stdlib.h>
 #include <string.h>
 
 #include "kmpb_internal.h"
 
-#define N_BUCKET 7        /* pattern buckets; bit 7 of every depth belongs to the NUL detector */
+#define N_BUCKET 5        /* pattern buckets; the sixth bit of every field belongs to the NUL detector */
 #define FILTER_DEPTH 4
 #define TEXT_ALPHABET 96.0 /* cost model only: distinct byte values expected in payload text */
 #define DP_LIMIT 1024      /* above this many distinct patterns the bucket split is not optimised */
@@ -251,23 +253,16 @@ static double build_filter_words(uint32_t n_uniq, pat_ref *uniq, uint32_t n_buck
     return estimate;
 }
 
-static void build_filter(kmpb_tables *t, pat_ref *uniq)
-{
-    t->filter_fp_estimate = build_filter_words(t->n_uniq, uniq, N_BUCKET, 8, t->filter);
-    /* bucket 7: stages 0..2 always pass, stage 3 passes on NUL only -> bit 31 of the running
-     * shift-and word is set exactly on a NUL byte */
-    for (uint32_t c = 0; c < 256; c++) t->filter[c] |= 0x00808080u;
-    t->filter[0] |= 0x80000000u;
-    t->bucket_of_uniq_valid = 1;
-}
-
-/* The same prefilter in the geometry a two-bytes-per-update kernel needs (not used by the
- * shipped kernels yet): five fields of 6 bits -- depths 0..3 and a fifth field that passes everything, so that a
- * report lingers one step -- with 5 pattern buckets (bits 0..4 of a field) and the NUL detector in bit 5 (depths
- * 0..2 always pass, depth 3 passes on NUL only).  One update per byte: S = ((S << 6) | 0x3f) & words[c]; bits 18..22
- * report the windows that end at this byte, bits 24..28 those that ended at the byte before.  Two bytes per update:
+/* The prefilter in the geometry the union kernel uses: five fields of 6 bits -- depths 0..3 and a fifth field that
+ * passes everything, so that a report lingers one step -- with 5 pattern buckets (bits 0..4 of a field) and the NUL
+ * detector in bit 5 (depth 0 passes on NUL only, depths 1..3 always: it reports three bytes after the NUL, when a
+ * pattern starting at the NUL would report).  One update per byte: S = ((S << 6) | 0x3f) & words[c]; bits 18..22
+ * report the windows that end at this byte, bit 23 "the byte three back is NUL", bits 24..29 the same for the byte
+ * before.  Two bytes per update (what the row loop does):
  *   S = ((S << 12) | 0xfff) & ((words[b0] << 6) | 0x3f) & words[b1]
- * which is the same function (tests/c/test_tables.c checks it), bits 24..28 then being byte b0's reports. */
+ * which is the same function (tests/c/test_tables.c checks it), bits 24..29 then being byte b0's reports.
+ * The bucket split starts from the optimal contiguous split of the patterns sorted by (min(len, 4), content) and is
+ * refined by hill climbing (moves and swaps) on the estimated candidate probability. */
 int kmpb_filter6_build(const kmpb_tables *t, uint32_t words[256], double *estimate)
 {
     pat_ref *uniq = malloc((t->n_uniq ? t->n_uniq : 1) * sizeof *uniq);
@@ -277,7 +272,7 @@ int kmpb_filter6_build(const kmpb_tables *t, uint32_t words[256], double *estima
         uniq[u].len = t->uniq_len[u];
         uniq[u].index = u;
     }
-    const double e = build_filter_words(t->n_uniq, uniq, 5, 6, words);
+    const double e = build_filter_words(t->n_uniq, uniq, N_BUCKET, 6, words);
     free(uniq);
     /* the NUL detector: depth 0 passes on NUL only, depths 1..3 always -- it reports three bytes after the NUL, when a
      * pattern starting at the NUL would report, so that a report's "candidate" and "NUL" bits speak of the same byte */
@@ -551,10 +546,7 @@ int kmpb_tables_build_ex(kmpb_tables *t, const uint8_t *blob, const uint32_t *pa
 
     int rc = with_dfa ? build_dfa(t) : KMPB_OK;
     if (rc == KMPB_OK) rc = build_verify_tables(t);
-    if (rc == KMPB_OK) {
-        build_filter(t, uniq);
-        rc = kmpb_filter6_build(t, t->filter6, &t->filter6_fp_estimate);
-    }
+    if (rc == KMPB_OK) rc = kmpb_filter6_build(t, t->filter6, &t->filter6_fp_estimate);
     free(uniq);
     if (rc != KMPB_OK) kmpb_tables_free(t);
     return rc;

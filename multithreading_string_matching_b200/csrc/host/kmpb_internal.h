@@ -44,17 +44,12 @@ typedef struct kmpb_tables {
     uint32_t *out_head;      /* [n_state+1] */
     uint32_t *out_id;
 
-    /* shift-and prefilter (kernel B): for byte value c, filter[c] has bit (8*d + b) set when some
-     * pattern of bucket b has byte c at depth d (or is shorter than d+1 bytes); bucket 7 of depth 3
-     * is the NUL detector, buckets 7 of depths 0..2 are always set */
-    uint32_t filter[256];
-    uint32_t bucket_of_uniq_valid; /* 1 when filter[] is usable (n_uniq > 0) */
-
-    /* the same prefilter in the geometry the union kernel uses (automaton.c kmpb_filter6_build): five fields of 6 bits
-     * (depths 0..3 and a field in which a report lingers one step), 5 pattern buckets + the NUL detector, so that the
-     * kernel updates its state once per two bytes */
+    /* shift-and prefilter (automaton.c kmpb_filter6_build): for byte value c, filter6[c] has bit (6*d + b) set when some
+     * pattern of bucket b (0..4) has byte c at depth d (0..3) or is shorter than d+1 bytes; bit 5 of depth 0 is set for
+     * c == 0 only and bit 5 of depths 1..3 always (the NUL detector); bits 24..29 always (a report lingers one step, so
+     * that the kernel can update its state once per two bytes) */
     uint32_t filter6[256];
-    double filter6_fp_estimate;
+    double filter6_fp_estimate;    /* estimated candidate probability per text byte, uniform bytes */
 
     /* start-anchored verification tables (the device's slow path): two probe tables -- A for the two-byte patterns,
      * keyed by their two bytes, B for the patterns of three and more bytes, keyed by their first three -- of slots
@@ -70,7 +65,6 @@ typedef struct kmpb_tables {
      *   pattern words: every pattern zero-padded to a multiple of 4 bytes */
     uint32_t *vtab;
     uint32_t vtab_words;
-    double filter_fp_estimate;     /* estimated candidate probability per text byte, uniform bytes */
 } kmpb_tables;
 
 /* pcap_csr.c, used by the streamed savefile path (api.cu): end of the chunk of whole packets that starts at
@@ -85,7 +79,7 @@ uint32_t kmpb_vtab_slot(uint32_t key, uint32_t shift);
 int kmpb_tables_build(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat);
 /* ... and, with_dfa != 0, the merged automaton of all patterns the table tests compare against (never uploaded) */
 int kmpb_tables_build_ex(kmpb_tables *t, const uint8_t *blob, const uint32_t *pat_off, uint32_t n_pat, int with_dfa);
-/* the prefilter in 6-bit fields (5 pattern buckets + NUL, depth 4 + a lingering field): automaton.c, DESIGN.md section 10 */
+/* the prefilter words (5 pattern buckets + NUL in 6-bit fields, depth 4 + a lingering field): automaton.c */
 int kmpb_filter6_build(const kmpb_tables *t, uint32_t words[256], double *estimate);
 void kmpb_tables_free(kmpb_tables *t);
 
