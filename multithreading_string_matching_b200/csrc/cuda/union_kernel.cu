@@ -8,7 +8,7 @@
 //  holds bytes [32 l, 32 l + 32) of the row in eight registers; UN_NBUF such row buffers rotate (the loop is
 //  unrolled UN_NBUF times, so the rotation costs no moves) and an L2 prefetch runs UN_PF rows ahead of the
 //  loads.  The four bytes a lane needs after its own come from the next lane's first register (one SHFL); lane
-//  31 loads the eight bytes after the row itself.  (Round 1 staged the rows in a shared-memory ring filled by
+//  31 loads the four bytes after the row itself.  (Round 1 staged the rows in a shared-memory ring filled by
 //  cp.async: ring write + read-back cost 17-28 shared-memory wavefronts per row next to the filter's 35.)
 //  Each lane pushes its 32 bytes (+4 bytes of lookahead) through a 4-byte-deep shift-and filter over 5 pattern
 //  buckets and a NUL detector, in 6-bit fields with a fifth field in which a report lingers one step, so that
@@ -22,15 +22,19 @@
 //  bytes (or all the bytes) of some pattern of bucket b", bits 18..22 the same for b1; bits 29 / 23 say "the
 //  byte three before b0 / b1 is NUL" (the NUL detector reports as late as a pattern that starts at the NUL
 //  would, which keeps "what starts here" and "is this a NUL" of a byte in the same report).  The reports are
-//  OR-ed per quarter of the group (8 start positions); a lane with any report appends an EVENT -- its 32 bytes
-//  and the 8 after them, where they are, and which quarters reported -- to the warp's list in shared memory; a
-//  lane with two reporting quarters appends two events, one per quarter, so that the resolve step re-examines
-//  one quarter per event.  That is all: two ballots and (usually) a few stores per row on top of the filter.
-//  (NUL-dense rows: events that hold only NULs and are superseded by a later one of the same row are dropped
-//  first, drop_superseded.)
+//  OR-ed per quarter of the group (8 start positions); a lane with any report appends an EVENT -- eight bytes: which
+//  group of the item it is (| the item's parity << 31) and which quarters reported what -- to the warp's ring in
+//  shared memory.  That is all: one ballot and one 8-byte store per reporting lane on top of the filter.  An event
+//  carries no text: the resolve step fetches the 36 bytes it needs again, from L2 (the row was read a few
+//  microseconds ago), which is cheaper than writing 48 bytes per event from the row loop and keeps the loop's
+//  registers free of the lookahead words.  (NUL-dense rows: events that hold only NULs and are superseded by a
+//  later one of the same row are dropped first, drop_superseded.)
 //
-//  SLOW PATH (events only).  The list is a ring of UN_QCAP slots; whenever it holds 32 events, the warp -- after
-//  it has issued the loads of the next rows -- resolves the 32 oldest at once, in stream order, one per lane:
+//  SLOW PATH (events only).  The ring has UN_QCAP slots; whenever it holds 32 events, the warp -- at the top of the
+//  row loop, the ONE place the resolve step is inlined (a call from inside the loop made ptxas spill five of the
+//  loop's values around it; the item switch and the final flush call a not-inlined copy) -- resolves the 32 oldest
+//  at once, in stream order, one per lane:
+//  Phase 0: the lane fetches its event's group (32 B + 4 B lookahead) into the warp's staging area.
 //  Phase 1:
 //    - the lane re-runs the filter over the quarter that reported, this time recording which start positions
 //      fired and which bytes are NUL;
@@ -75,10 +79,11 @@ constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item si
 #define KMPB_UN_TAIL_ITEMS 16384
 #endif
 constexpr uint32_t UN_TAIL_ITEMS = KMPB_UN_TAIL_ITEMS;   // small items at the end of a batch (about one per warp x 4)
-constexpr uint32_t UN_QCAP = 64;    // slots of a warp's event ring (fewer than 32 pending + at most 32 of a row)
+constexpr uint32_t UN_QCAP = 128;   // slots of a warp's event ring (fewer than 32 pending + at most 32 of each of two rows)
 constexpr uint32_t UN_QDRAIN = 32;  // events resolved at once (one per lane)
-constexpr uint32_t UN_Q_WORDS = 12; // event: 32 B group, 4 B lookahead, -, group index | item parity << 31, quarter reports (48 B)
-constexpr uint32_t UN_Q_BYTES1 = UN_Q_WORDS * 4;
+constexpr uint32_t UN_Q_BYTES1 = 8; // an event in the ring: group index | item parity << 31, quarter reports
+constexpr uint32_t UN_T_WORDS = 12; // an event being resolved: 32 B group, 4 B lookahead, next boundary, group index | parity, boundaries
+constexpr uint32_t UN_T_BYTES1 = UN_T_WORDS * 4;
 #ifndef KMPB_UN_DENSE
 #define KMPB_UN_DENSE 8
 #endif
@@ -86,12 +91,14 @@ constexpr uint32_t UN_DENSE = KMPB_UN_DENSE; // reporting groups per row from wh
 constexpr uint32_t UN_LUT_BYTES = 256 * 128; // one table: a 128-byte row (32 lanes x 4 bytes) per byte value
 constexpr uint32_t FULL = 0xffffffffu;
 
-// Dynamic shared memory: L, G, the event rings, the warps' scratch words, the counters (if they fit), the probe
-// tables (if they fit).
+// Dynamic shared memory: L, G, the event rings, the events being resolved, the warps' scratch words, the counters (if
+// they fit), the probe tables (if they fit).
 constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_BYTES1;
+constexpr uint32_t UN_T_BYTES = UN_WARPS * UN_QDRAIN * UN_T_BYTES1; // the 32 events a warp is resolving, with their text
 constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
 constexpr uint32_t UN_OFF_Q = 2 * UN_LUT_BYTES;
-constexpr uint32_t UN_OFF_SCRATCH = UN_OFF_Q + UN_Q_BYTES;
+constexpr uint32_t UN_OFF_T = UN_OFF_Q + UN_Q_BYTES;
+constexpr uint32_t UN_OFF_SCRATCH = UN_OFF_T + UN_T_BYTES;
 constexpr uint32_t UN_OFF_MISC = UN_OFF_SCRATCH + UN_SCRATCH_BYTES; // 128 bytes: what the resolve step reads of the
                                                                     // launch parameters (DC_*), the "last block" flag
 constexpr uint32_t UN_OFF_COUNTS = UN_OFF_MISC + 128;
@@ -305,7 +312,7 @@ enum { DC_TEXT_LO = 0, DC_TEXT_HI,   // p.bytes - p.abs_base: absolute byte 0
 //   [b_rel, e_rel) relative to row0 = the absolute position of its first row, 1 + the (relative) position of the last
 //   NUL byte among its events resolved so far (0: none), and either 0x80000000 | L when all its packets have L bytes or
 //   (ke - ks) / (e_rel - b_rel) as a float (the interpolation guess of the packet lookup) --
-// then, at byte 64, {parity of the item being scanned, "the list holds events of the item before it"}.
+// then, at byte 64, {parity of the item being scanned, how many of the pending events belong to items before it}.
 constexpr uint32_t SC_STATE = 64;
 
 extern __shared__ __align__(1024) uint8_t smem[];
@@ -323,6 +330,7 @@ __device__ __forceinline__ const uint8_t *dc_ptr(uint32_t k)
     return reinterpret_cast<const uint8_t *>(((uint64_t)v.y << 32) | v.x);
 }
 __device__ __forceinline__ uint32_t warp_q_sa() { return smem_sa() + UN_OFF_Q + (threadIdx.x >> 5) * (UN_QCAP * UN_Q_BYTES1); }
+__device__ __forceinline__ uint32_t warp_t_sa() { return smem_sa() + UN_OFF_T + (threadIdx.x >> 5) * (UN_QDRAIN * UN_T_BYTES1); }
 __device__ __forceinline__ uint32_t warp_scratch_sa() { return smem_sa() + UN_OFF_SCRATCH + (threadIdx.x >> 5) * 128; }
 
 // what a resolve step needs besides the events; every warp derives it from its own index (nothing of it has to live in
@@ -426,7 +434,7 @@ __device__ __forceinline__ void verify_start(const drain_args &d, const probe_co
 // event carries its item's parity, and what the resolve step has to know about either item waits in the warp's
 // scratch words, where the warp put it when it took the item: no lane has to look anything up in global memory for
 // it, and the row loop does not keep it in registers.  Positions are relative to the item's row0 (32 bits).
-__device__ __noinline__ void drain_events(const uint32_t head, const uint32_t n)
+__device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n)
 {
     drain_args d;
     d.q_sa = warp_q_sa();
@@ -438,17 +446,34 @@ __device__ __noinline__ void drain_events(const uint32_t head, const uint32_t n)
     uint32_t lt;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     __syncwarp();
-    const uint32_t entry_sa = d.q_sa + ((head + lane) & (UN_QCAP - 1)) * UN_Q_BYTES1;
+    const uint32_t t_sa = warp_t_sa();
+    const uint32_t entry_sa = t_sa + lane * UN_T_BYTES1; // my event's slot among the 32 being resolved
     uint32_t cm = 0, zm = 0, gq = 0, par = 0;
     uint32_t ks = 0, ke = 0, b_rel = 0, e_rel = 0, row0_lo = 0, carry = 0, psize = 0;
     if (lane < n) {
-        const uint2 t = lds64v(entry_sa + 40); // group index (relative to row0) | item parity << 31, quarter reports
+        const uint2 t = lds64v(d.q_sa + ((head + lane) & (UN_QCAP - 1)) * UN_Q_BYTES1); // group index (relative to row0) | item parity << 31, quarter reports
         par = t.x >> 31;
         gq = (t.x & 0x7fffffffu) << 5;
         const uint32_t set_sa = d.scratch_sa + (par << 5); // my item's scratch set
         const uint4 s0 = lds128v(set_sa), s1 = lds128v(set_sa + 16);
         ks = s0.x; ke = s0.y; b_rel = s0.z; e_rel = s0.w;
         row0_lo = s1.x; carry = s1.z; psize = s1.w;
+        {   // The event's 32 bytes and the 4 after them, from L2 (the row was read a few microseconds ago) into its slot:
+            // the row loop stores 8 bytes per event instead of 48 and keeps no row in registers for it.  A group at or
+            // past the item's end reported from registers that were not loaded and holds nothing of this item.
+            uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;
+            uint32_t g2 = 0;
+            if (gq < e_rel) {
+                const uint8_t *src = dc_ptr(DC_TEXT_LO) + (((uint64_t)s1.y << 32) | s1.x) + gq;
+                g0 = __ldg(reinterpret_cast<const uint4 *>(src));
+                g1 = __ldg(reinterpret_cast<const uint4 *>(src + 16));
+                if (gq + UN_GRP < ((e_rel + 31u) & ~31u)) g2 = __ldg(reinterpret_cast<const uint32_t *>(src + 32));
+            }
+            sts128v(entry_sa, g0.x, g0.y, g0.z, g0.w);
+            sts128v(entry_sa + 16, g1.x, g1.y, g1.z, g1.w);
+            sts64v(entry_sa + 32, g2, 0u);
+            sts32v(entry_sa + 40, t.x);
+        }
         // Re-run the filter over the quarters that reported (usually one), one byte per update, this time recording
         // which start positions fired and which bytes are NUL.  Quarter k: bytes 8k..8k+11 -- three bytes of run-in,
         // then the starts 8k..8k+8 report at the bytes 8k+3..8k+11, and so do the NULs among the bytes 8k..8k+8 (the
@@ -594,7 +619,7 @@ __device__ __noinline__ void drain_events(const uint32_t head, const uint32_t n)
         if (t < total) {
             for (uint32_t j = first; j < t; j++) m &= m - 1;
             const uint32_t i = __ffs(m) - 1;
-            const uint32_t owner_sa = d.q_sa + ((head + l) & (UN_QCAP - 1)) * UN_Q_BYTES1;
+            const uint32_t owner_sa = t_sa + l * UN_T_BYTES1;
             const uint32_t onext = lds32v(owner_sa + 36), obm = lds32v(owner_sa + 44);
             const uint32_t above = obm & ~((2u << i) - 1u); // packet starts after byte i
             const uint32_t room = (above ? (uint32_t)__ffs(above) - 1u : onext) - i;
@@ -604,6 +629,10 @@ __device__ __noinline__ void drain_events(const uint32_t head, const uint32_t n)
     }
     __syncwarp();
 }
+
+// the same out of line, for the places that are not in the row loop (taking an item, the end of the batch): a call in
+// the row loop itself would cost that loop five spilled registers (the callee's needs bind at every call site)
+__device__ __noinline__ void drain_events(const uint32_t head, const uint32_t n) { drain_body(head, n); }
 
 // NUL-dense row.  An event without candidates exists only to tell later candidates where the last NUL before them
 // is; when the next event of the row is of the same kind, that one tells them a later NUL and this one is not needed:
@@ -666,7 +695,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     uint32_t qs = 0;
     auto pending = [&]() -> uint32_t { return qs >> 16; };
 
-    // resolve the oldest min(pending, 32) events
+    // resolve the oldest min(pending, 32) events (out of line: the rare places)
     auto resolve_oldest = [&]() {
         const uint32_t qn = qs >> 16, n = qn < UN_QDRAIN ? qn : UN_QDRAIN;
         drain_events((qs - qn) & (UN_QCAP - 1), n);
@@ -690,9 +719,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         // set still belongs to the item before the previous one; its events are gone unless the list has not been
         // resolved since then (the flag: "the list holds events of the item before the one being scanned"), in
         // which case they are now.
-        const uint2 st = lds64v(warp_scratch_sa() + SC_STATE); // parity of the previous item, pending flag
+        const uint2 st = lds64v(warp_scratch_sa() + SC_STATE); // parity of the previous item, pending events older than it
         const uint32_t par = st.x ^ 1u;
-        if (pending() && st.y)
+        if (st.y) // (the row loop counts them down as it resolves; an item of many rows leaves none)
             while (pending()) resolve_oldest();
         __syncwarp();
         const uint64_t row0 = b_abs & ~127ull; // absolute position of the item's first row
@@ -710,7 +739,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             const uint32_t set_sa = warp_scratch_sa() + (par << 5);
             sts128v(set_sa, ks, ke, b_rel, e_rel);
             sts128v(set_sa + 16, (uint32_t)row0, (uint32_t)(row0 >> 32), 0u, psize);
-            sts64v(warp_scratch_sa() + SC_STATE, par, pending() ? 1u : 0u);
+            sts64v(warp_scratch_sa() + SC_STATE, par, pending());
         }
         // The loop state of a lane, kept small (the filter needs the registers):
         //   src  = its 32 bytes of the row being scanned,
@@ -781,25 +810,17 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                     tp = drop_superseded(tops, m, ((t2 & 0x7c7c7c7cu) | (t3 & 0x1f1f1f1fu)) != 0);
                     mp = __ballot_sync(FULL, tp != 0);
                 }
-                // the ring takes it: fewer than 32 events were pending, a row appends at most 32
+                // the ring takes it: fewer than 32 events were pending at the top of the loop, a row appends at most 32
                 if (tp != 0) {
                     uint32_t lt;
                     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
                     const uint32_t e = q_sa + ((qs + __popc(mp & lt)) & (UN_QCAP - 1)) * UN_Q_BYTES1;
-                    sts128v(e, b.w[0], b.w[1], b.w[2], b.w[3]);
-                    sts128v(e + 16, b.w[4], b.w[5], b.w[6], b.w[7]);
-                    sts128v(e + 32, la, 0u, gcur, tp);
+                    sts64v(e, gcur, tp); // where and what; the resolve step fetches the bytes
                 }
                 qs += __popc(mp) * 0x10001u;
             }
             // the buffer is free: the row UN_NBUF ahead goes into it
             load_row(UN_NBUF, b);
-            // with the loads on their way: resolve 32 events if there are that many (no event of the item before this
-            // one is left afterwards: there were fewer than 32 of them when this item was taken)
-            if (qs >= (UN_QDRAIN << 16)) {
-                resolve_oldest();
-                if (lane == 0) sts32v(warp_scratch_sa() + SC_STATE + 4, 0u);
-            }
         };
 
         // the first UN_PF rows' lines: 128 bytes per lane and step
@@ -826,6 +847,17 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         };
 #pragma unroll 1
         for (;;) {
+            // With the loads of the next two rows on their way: resolve 32 events while there are that many -- here and
+            // nowhere else in the loop, inlined (one copy of the code, and no call whose register needs the loop would
+            // have to respect).
+            while (qs >= (UN_QDRAIN << 16)) {
+                drain_body((qs - (qs >> 16)) & (UN_QCAP - 1), UN_QDRAIN);
+                qs -= UN_QDRAIN << 16;
+                if (lane == 0) { // that many fewer events of older items
+                    const uint32_t older = lds32v(warp_scratch_sa() + SC_STATE + 4);
+                    sts32v(warp_scratch_sa() + SC_STATE + 4, older > UN_QDRAIN ? older - UN_QDRAIN : 0u);
+                }
+            }
             scan_row(b0);
             if (advance()) break;
             scan_row(b1);
