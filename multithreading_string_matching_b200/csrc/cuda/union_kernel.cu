@@ -52,11 +52,12 @@
 //  counted exactly once.  Counts go to shared-memory counters and leave the block as one atomic per
 //  distinct pattern.  No separators, no padding and no second pass over the payload.
 #include <algorithm>
+#include <type_traits>
 
 #include "kmpb_device.cuh"
 
 #ifndef KMPB_UN_THREADS
-#define KMPB_UN_THREADS 896
+#define KMPB_UN_THREADS 1024
 #endif
 #ifndef KMPB_UN_ITEM_KB
 #define KMPB_UN_ITEM_KB 64
@@ -80,7 +81,11 @@ constexpr uint32_t UN_ITEM_BYTES = KMPB_UN_ITEM_KB << 10; // target work-item si
 #endif
 constexpr uint32_t UN_TAIL_ITEMS = KMPB_UN_TAIL_ITEMS;   // small items at the end of a batch (about one per warp x 4)
 constexpr uint32_t UN_QCAP = 128;   // slots of a warp's event ring (fewer than 32 pending + at most 32 of each of two rows)
-constexpr uint32_t UN_QDRAIN = 32;  // events resolved at once (one per lane)
+#ifndef KMPB_UN_QDRAIN
+#define KMPB_UN_QDRAIN 32
+#endif
+constexpr uint32_t UN_QDRAIN = KMPB_UN_QDRAIN; // events resolved at once (one per lane)
+static_assert(UN_QDRAIN >= 8 && UN_QDRAIN <= 32, "one event per lane");
 constexpr uint32_t UN_Q_BYTES1 = 8; // an event in the ring: group index | item parity << 31, quarter reports
 constexpr uint32_t UN_T_WORDS = 12; // an event being resolved: 32 B group, 4 B lookahead, next boundary, group index | parity, boundaries
 constexpr uint32_t UN_T_BYTES1 = UN_T_WORDS * 4;
@@ -190,12 +195,13 @@ struct row_regs {
 // 32 bytes global -> registers in one instruction (SASS LDG.E.256, sm_100), L1 not allocated (the row is used once),
 // under a predicate; a lane that does not load keeps what its registers held (an older row of the same item,
 // or zeros): whatever it reports from them lies past the item's end and is cut by the resolve step
+template <uint32_t OFF>
 __device__ __forceinline__ void ldg256_if(bool on, row_regs &b, const void *src)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
-                 "@p ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t}"
+                 "@p ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+%10];\n\t}"
                  : "+r"(b.w[0]), "+r"(b.w[1]), "+r"(b.w[2]), "+r"(b.w[3]), "+r"(b.w[4]), "+r"(b.w[5]), "+r"(b.w[6]), "+r"(b.w[7])
-                 : "l"(src), "r"((uint32_t)on));
+                 : "l"(src), "r"((uint32_t)on), "n"(OFF));
 }
 // 4 bytes under a predicate (lane 31's lookahead); 0 otherwise
 __device__ __forceinline__ uint32_t ldg32_if(bool on, const void *src)
@@ -211,6 +217,11 @@ __device__ __forceinline__ uint32_t ldg32_if(bool on, const void *src)
 __device__ __forceinline__ void prefetch_l2_if(bool on, const void *src)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p prefetch.global.L2 [%0];\n\t}" ::"l"(src), "r"((uint32_t)on) : "memory");
+}
+template <uint32_t OFF>
+__device__ __forceinline__ void prefetch_l2_if(bool on, const void *src)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p prefetch.global.L2 [%0+%2];\n\t}" ::"l"(src), "r"((uint32_t)on), "n"(OFF) : "memory");
 }
 // pointer + 32-bit offset as IMAD.WIDE.U32 (FMA pipe), not IADD3 + IADD3.X (ALU pipe)
 __device__ __forceinline__ const uint8_t *add_wide(const uint8_t *base, uint32_t offset)
@@ -687,19 +698,25 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     __syncthreads();
 
         static_assert(UN_LUT_BYTES == 32768, "lds32_g's immediate offset");
-    const uint32_t lutL = saddr_of(lut) + (lane << 2);
+    uint32_t lutL = smem_sa() + (lane << 2); // L starts the dynamic shared memory
+    asm volatile("" : "+r"(lutL));             // opaque: a value to keep in its register, not an expression to recompute
     const uint32_t mul2 = p.mul4096;
     const uint32_t q_sa = warp_q_sa();
-    // the event ring's state in one register: pending events << 16 | ring slot the next one goes to (mod 2^16; the
-    // oldest pending event sits at slot (next - pending) mod UN_QCAP)
+    // The event ring's state in one register: byte offset in the ring of the slot the next event goes to << 22 | pending
+    // events.  The ring is 2^10 bytes, so the offset wraps by falling off the top of the word (however many events a
+    // warp sees in a launch) and an address is ring + (state >> 22); the oldest pending event sits `pending` slots
+    // before the next one.
+    static_assert(UN_QCAP * UN_Q_BYTES1 == 1024, "the ring offset lives in the top 10 bits of qs");
+    constexpr uint32_t QS_SLOT = UN_Q_BYTES1 << 22, QS_PENDING = (1u << 22) - 1u;
     uint32_t qs = 0;
-    auto pending = [&]() -> uint32_t { return qs >> 16; };
+    auto pending = [&]() -> uint32_t { return qs & QS_PENDING; };
+    auto oldest = [&]() -> uint32_t { return ((qs >> 22) / UN_Q_BYTES1 - pending()) & (UN_QCAP - 1); };
 
     // resolve the oldest min(pending, 32) events (out of line: the rare places)
     auto resolve_oldest = [&]() {
-        const uint32_t qn = qs >> 16, n = qn < UN_QDRAIN ? qn : UN_QDRAIN;
-        drain_events((qs - qn) & (UN_QCAP - 1), n);
-        qs -= n << 16;
+        const uint32_t qn = pending(), n = qn < UN_QDRAIN ? qn : UN_QDRAIN;
+        drain_events(oldest(), n);
+        qs -= n;
     };
 
     for (;;) {
@@ -754,11 +771,11 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         // 256-bit load.  Rows past the item's end and the lanes past load_end in its last row load nothing and keep
         // what they held: whatever they report from it is cut to the item's byte range by the resolve step.  The L2
         // prefetch of the row UN_PF rows further on rides on the same address.
-        auto load_row = [&](const uint32_t ahead, row_regs &b) {
+        auto load_row = [&](auto ahead_c, row_regs &b) {
+            constexpr uint32_t ahead = decltype(ahead_c)::value;
             const int32_t l = left - (int32_t)(ahead * UN_ROW);
-            const uint8_t *s = src + ahead * UN_ROW;
-            ldg256_if(l > 0, b, s);
-            if (UN_PF) prefetch_l2_if(l > (int32_t)(UN_PF * UN_ROW), s + UN_PF * UN_ROW);
+            ldg256_if<ahead * UN_ROW>(l > 0, b, src);
+            if (UN_PF) prefetch_l2_if<(ahead + UN_PF) * UN_ROW>(l > (int32_t)(UN_PF * UN_ROW), src);
         };
 
         // one row: filter its bytes, append the events, refill the buffer with the row UN_NBUF ahead, and resolve
@@ -766,8 +783,13 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         auto scan_row = [&](row_regs &b) {
             // the 4 bytes after my group: the next lane's first word; for lane 31 the first word of the next row, asked
             // for now (the row's own load is already on its way, so it comes from L2 or rides on that fill) and used last
-            const uint32_t la31 = ldg32_if(lane == 31 && left > (int32_t)UN_GRP, src + UN_GRP);
-            uint32_t la = __shfl_down_sync(FULL, b.w[0], 1);
+            uint32_t la;
+            asm volatile("{\n\t.reg .pred p, q;\n\t"
+                         "shfl.sync.down.b32 %0|p, %1, 1, 0x1f, 0xffffffff;\n\t" // p: there is a lane above me
+                         "setp.gt.and.s32 q, %2, 32, !p;\n\t"
+                         "@q ld.global.L1::no_allocate.u32 %0, [%3+32];\n\t}"
+                         : "=&r"(la)
+                         : "r"(b.w[0]), "r"(left), "l"(src));
 
             // ---- shift-and filter over 36 bytes, two per update ---------------------------------------
             // Update j takes bytes 2j, 2j+1 and reports what starts at 2j-3 (bits 24..29) and 2j-2 (bits 18..23): the
@@ -789,9 +811,8 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             acc2 |= SA2(b.w[6], 2);                 // 23, 24
             acc3 = SA2(b.w[7], 0);                  // 25, 26
             acc3 |= SA2(b.w[7], 2);
-            la = lane == 31 ? la31 : la;
             acc3 |= SA2(la, 0);                     // 29, 30
-            SA2(la, 2);                             // 31 | 32: the next lane's
+            S = (S * mul2 + 4095u) & LUT_G(la, 2);  // 31 (start 32 is the next lane's: no lookup for the second byte)
             acc3 |= S & F6_HI;
             // The reports of quarter k: byte 3 of acc[k] (b0's, bits 0..5) and byte 2 (b1's, bits 2..7), the four
             // quarters side by side; quarter k has something to resolve iff byte k of `tops` is nonzero.
@@ -803,24 +824,24 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
 #ifdef KMPB_ABLATE_SLOW_PATH // measurement only (wrong counts): how fast is the fast path alone?
             if (m == 0x12345678u)
 #endif
-            if (m) {
-                uint32_t tp = tops, mp = m;
-                if (UN_DENSE <= 32 && __popc(m) >= (int)UN_DENSE) {
+            {   // (no test for "no reports at all": one row in 500)
+                uint32_t tp = tops, mp = m, n = __popc(m);
+                if (UN_DENSE <= 32 && n >= UN_DENSE) {
                     // NUL-dense row: superseded NUL-only events are dropped first (a rare path of its own)
                     tp = drop_superseded(tops, m, ((t2 & 0x7c7c7c7cu) | (t3 & 0x1f1f1f1fu)) != 0);
                     mp = __ballot_sync(FULL, tp != 0);
+                    n = __popc(mp);
                 }
                 // the ring takes it: fewer than 32 events were pending at the top of the loop, a row appends at most 32
                 if (tp != 0) {
                     uint32_t lt;
                     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
-                    const uint32_t e = q_sa + ((qs + __popc(mp & lt)) & (UN_QCAP - 1)) * UN_Q_BYTES1;
-                    sts64v(e, gcur, tp); // where and what; the resolve step fetches the bytes
+                    sts64v(q_sa + ((qs + __popc(mp & lt) * QS_SLOT) >> 22), gcur, tp); // where and what; the resolve step fetches the bytes
                 }
-                qs += __popc(mp) * 0x10001u;
+                qs += n * (QS_SLOT + 1u);
             }
             // the buffer is free: the row UN_NBUF ahead goes into it
-            load_row(UN_NBUF, b);
+            load_row(std::integral_constant<uint32_t, UN_NBUF>{}, b);
         };
 
         // the first UN_PF rows' lines: 128 bytes per lane and step
@@ -828,31 +849,32 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             for (uint32_t x = lane * 128u; x < UN_PF * UN_ROW; x += 4096u) prefetch_l2_if(x < load_end, src - lane * UN_GRP + x);
         // UN_NBUF rows per trip: the buffers are compile-time registers, no moves between them
         row_regs b0 = {}, b1 = {};
-        load_row(0, b0);
-        load_row(1, b1);
+        load_row(std::integral_constant<uint32_t, 0>{}, b0);
+        load_row(std::integral_constant<uint32_t, 1>{}, b1);
 #if KMPB_UN_NBUF >= 3
         row_regs b2 = {};
-        load_row(2, b2);
+        load_row(std::integral_constant<uint32_t, 2>{}, b2);
 #endif
 #if KMPB_UN_NBUF >= 4
         row_regs b3 = {};
-        load_row(3, b3);
+        load_row(std::integral_constant<uint32_t, 3>{}, b3);
 #endif
         // next row; the item is through when lane 0 has nothing left (its rows start at multiples of 32)
         auto advance = [&]() -> bool {
             src += UN_ROW;
             left -= (int32_t)UN_ROW;
             gcur += UN_ROW / UN_GRP;
-            return left + (int32_t)(lane * UN_GRP) <= 0;
+            // left + 32 * lane <= 0, with 32 * lane = 8 * (lutL - start of L): no lane index to recompute
+            return (left >> 3) + (int32_t)(lutL - smem_sa()) <= 0;
         };
 #pragma unroll 1
         for (;;) {
             // With the loads of the next two rows on their way: resolve 32 events while there are that many -- here and
             // nowhere else in the loop, inlined (one copy of the code, and no call whose register needs the loop would
             // have to respect).
-            while (qs >= (UN_QDRAIN << 16)) {
-                drain_body((qs - (qs >> 16)) & (UN_QCAP - 1), UN_QDRAIN);
-                qs -= UN_QDRAIN << 16;
+            while (pending() >= UN_QDRAIN) {
+                drain_body(oldest(), UN_QDRAIN);
+                qs -= UN_QDRAIN;
                 if (lane == 0) { // that many fewer events of older items
                     const uint32_t older = lds32v(warp_scratch_sa() + SC_STATE + 4);
                     sts32v(warp_scratch_sa() + SC_STATE + 4, older > UN_QDRAIN ? older - UN_QDRAIN : 0u);
