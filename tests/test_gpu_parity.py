@@ -394,6 +394,31 @@ def test_sparse_events_over_many_work_items(matchers, oracle):
     assert m.count_host(hdata, hoff) == oracle.count_csr(hdata, hoff, pats)
 
 
+def test_more_events_per_warp_than_a_16_bit_counter_holds(matchers):
+    """Every 32-byte group of the stream raises an event (payloads of one repeated letter, the pattern is that letter
+    twice): ~80 000 events per warp of the union engine in one launch.  The event ring's state register must wrap
+    without touching its count of pending events (an earlier encoding carried into it after 65 536 events).  The
+    counts are known in closed form: a packet of L bytes holds L - 1 overlapping occurrences (serial.c:219 steps to
+    pi[q-1] after a match) and L - 2 of the three-letter pattern."""
+    import torch
+
+    n, L = 8_600_000, 1400  # 12 GB
+    free, _ = torch.cuda.mem_get_info()
+    if free < 16 * 2**30:
+        pytest.skip("needs 16 GB of device memory")
+    d_bytes = torch.full((n * L + 4096,), ord("a"), dtype=torch.uint8, device="cuda:0")
+    d_off = torch.arange(0, (n + 1) * L, L, dtype=torch.int64, device="cuda:0")
+    pats = [b"aa", b"aaa", b"ab"]
+    m = matchers["union"]
+    m.set_patterns(pats)
+    d_counts = torch.zeros(len(pats), dtype=torch.int64, device="cuda:0")
+    m.count_device(d_bytes.data_ptr(), d_off.data_ptr(), n, d_counts.data_ptr(), span=(0, n * L))
+    torch.cuda.synchronize()
+    assert d_counts.cpu().tolist() == [n * (L - 1), n * (L - 2), 0]
+    del d_bytes, d_off
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("engine", ["union", "perpat"])
 def test_fused_reduce_into_several_vectors(matchers, oracle, strings, engine):
     """kmpb_count_device_span_peers: the counts are added to every vector it is given -- by the union kernel's last
