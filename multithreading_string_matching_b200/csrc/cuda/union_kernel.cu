@@ -34,7 +34,8 @@
 //  row loop, the ONE place the resolve step is inlined (a call from inside the loop made ptxas spill five of the
 //  loop's values around it; the item switch and the final flush call a not-inlined copy) -- resolves the 32 oldest
 //  at once, in stream order, one per lane:
-//  Phase 0: the lane fetches its event's group (32 B + 4 B lookahead) into the warp's staging area.
+//  Phase 0 (issued one trip of the row loop earlier, cp.async: nobody waits for L2): the lane's event's group (32 B
+//  + 8 B lookahead) travels into the warp's staging area.
 //  Phase 1:
 //    - the lane re-runs the filter over the quarter that reported, this time recording which start positions
 //      fired and which bytes are NUL;
@@ -87,7 +88,7 @@ constexpr uint32_t UN_QCAP = 128;   // slots of a warp's event ring (fewer than 
 constexpr uint32_t UN_QDRAIN = KMPB_UN_QDRAIN; // events resolved at once (one per lane)
 static_assert(UN_QDRAIN >= 8 && UN_QDRAIN <= 32, "one event per lane");
 constexpr uint32_t UN_Q_BYTES1 = 8; // an event in the ring: group index | item parity << 31, quarter reports
-constexpr uint32_t UN_T_WORDS = 12; // an event being resolved: 32 B group, 4 B lookahead, next boundary, group index | parity, boundaries
+constexpr uint32_t UN_T_WORDS = 12; // an event being resolved: 32 B group, 8 B lookahead, group index | parity, packet boundaries in the group
 constexpr uint32_t UN_T_BYTES1 = UN_T_WORDS * 4;
 #ifndef KMPB_UN_DENSE
 #define KMPB_UN_DENSE 8
@@ -286,6 +287,23 @@ __device__ __forceinline__ void sts128v(uint32_t saddr, uint32_t a, uint32_t b, 
 {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// global -> shared without a register in between (SASS LDGSTS); `bytes` of the 16 (8) are read, the rest is zero-filled
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void sts8v(uint32_t saddr, uint32_t a) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(a) : "memory"); }
+__device__ __forceinline__ uint32_t lds8v(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // bits [lo, hi) of a 32-bit word, 0 <= lo, hi <= 32
@@ -323,8 +341,9 @@ enum { DC_TEXT_LO = 0, DC_TEXT_HI,   // p.bytes - p.abs_base: absolute byte 0
 //   [b_rel, e_rel) relative to row0 = the absolute position of its first row, 1 + the (relative) position of the last
 //   NUL byte among its events resolved so far (0: none), and either 0x80000000 | L when all its packets have L bytes or
 //   (ke - ks) / (e_rel - b_rel) as a float (the interpolation guess of the packet lookup) --
-// then, at byte 64, {parity of the item being scanned, how many of the pending events belong to items before it}.
-constexpr uint32_t SC_STATE = 64;
+// then, at byte 64, {parity of the item being scanned, how many of the pending events belong to items before it}, and at
+// byte 72 one byte per event being resolved: where the first packet boundary at or after the end of its group lies.
+constexpr uint32_t SC_STATE = 64, SC_NEXTB = 72;
 
 extern __shared__ __align__(1024) uint8_t smem[];
 // shared address of the dynamic shared memory (uniform registers; the generic-to-shared conversion costs more)
@@ -360,12 +379,12 @@ __device__ __forceinline__ void count_hit(const drain_args &d, uint32_t u)
 }
 
 // 4 text bytes starting at byte `pos` of the event at entry_sa, of which the first `need` (>= 1) matter: from
-// the event while its 36 bytes last, then from global memory (never past the word that holds the last
+// the event while its 40 bytes last, then from global memory (never past the word that holds the last
 // needed byte, which lies inside the packet).  Where the event's group lies in global memory follows from its
 // group index and its item's row0 in the warp's scratch words.
 __device__ __forceinline__ uint32_t text_window(const drain_args &d, uint32_t entry_sa, uint32_t pos, uint32_t need)
 {
-    if (pos + 4 <= 36) {
+    if (pos + 4 <= 40) {
         const uint32_t a = entry_sa + (pos & ~3u);
         return __funnelshift_r(lds32v(a), lds32v(a + 4), 8u * (pos & 3u));
     }
@@ -398,7 +417,7 @@ __device__ __forceinline__ void verify_start(const drain_args &d, const probe_co
         return VS ? lds64(d.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(vtab_g + word));
     };
     const uint32_t vt_one = pc.one, vt_slots_a = pc.slots_a, vt_slots_b = pc.slots_b;
-    // text bytes i..i+3 (always inside the event: i + 4 <= 36) and, if a pattern that long fits at all, i+4..i+7
+    // text bytes i..i+3 and, if a pattern that long fits at all, i+4..i+7 (both inside the event's 40 bytes)
     const uint32_t x0 = __funnelshift_r(lds32v(entry_sa + (i & ~3u)), lds32v(entry_sa + (i & ~3u) + 4), 8u * (i & 3u));
     if (vt_one) { // one-byte patterns: a direct table (room >= 1 always holds)
         const uint32_t u = vt(vt_one + (x0 & 0xffu));
@@ -434,6 +453,29 @@ __device__ __forceinline__ void verify_start(const drain_args &d, const probe_co
     }
 }
 
+// Phase 0 of a resolve step, on its own so that the row loop can issue it a row or two ahead: the n (<= 32) oldest
+// events' groups (32 B + 8 B lookahead), one per lane, from L2 (the rows were read a few microseconds ago) straight
+// into the warp's staging slots.  The row loop stores 8 bytes per event instead of 48 and keeps no row in registers
+// for it.  A group at or past its item's end reported from registers that were not loaded and holds nothing of the
+// item: zeros.  cp.async: no registers, and nobody waits here.
+__device__ __forceinline__ void drain_fetch(const uint32_t head, const uint32_t n)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane < n) {
+        const uint32_t tx = lds32v(warp_q_sa() + ((head + lane) & (UN_QCAP - 1)) * UN_Q_BYTES1);
+        const uint32_t gq = (tx & 0x7fffffffu) << 5;
+        const uint32_t set_sa = warp_scratch_sa() + ((tx >> 31) << 5); // the event's item
+        const uint32_t e_rel = lds32v(set_sa + 12);
+        const uint2 r0 = lds64v(set_sa + 16);
+        const bool in = gq < e_rel, more = in && gq + UN_GRP < ((e_rel + 31u) & ~31u);
+        const uint8_t *src = dc_ptr(DC_TEXT_LO) + (((uint64_t)r0.y << 32) | r0.x) + (in ? gq : 0u);
+        const uint32_t dst = warp_t_sa() + lane * UN_T_BYTES1;
+        cp_async16(dst, src, in ? 16u : 0u);
+        cp_async16(dst + 16, src + 16, in ? 16u : 0u);
+        cp_async8(dst + 32, more ? src + 32 : src, more ? 8u : 0u);
+    }
+}
+
 // Resolve the n (<= 32) oldest events of the warp's ring, which start at slot `head`.
 //
 // Phase 1, one event per lane: which start positions of the event's quarter(s) fired, where the NULs are, which
@@ -456,6 +498,7 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
     const uint32_t lutL = smem_sa() + (lane << 2), mul1 = dc(DC_MUL64);
     uint32_t lt;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    cp_async_wait_all(); // phase 0 (drain_fetch): my event's bytes are in its slot
     __syncwarp();
     const uint32_t t_sa = warp_t_sa();
     const uint32_t entry_sa = t_sa + lane * UN_T_BYTES1; // my event's slot among the 32 being resolved
@@ -469,22 +512,7 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
         const uint4 s0 = lds128v(set_sa), s1 = lds128v(set_sa + 16);
         ks = s0.x; ke = s0.y; b_rel = s0.z; e_rel = s0.w;
         row0_lo = s1.x; carry = s1.z; psize = s1.w;
-        {   // The event's 32 bytes and the 4 after them, from L2 (the row was read a few microseconds ago) into its slot:
-            // the row loop stores 8 bytes per event instead of 48 and keeps no row in registers for it.  A group at or
-            // past the item's end reported from registers that were not loaded and holds nothing of this item.
-            uint4 g0 = make_uint4(0, 0, 0, 0), g1 = g0;
-            uint32_t g2 = 0;
-            if (gq < e_rel) {
-                const uint8_t *src = dc_ptr(DC_TEXT_LO) + (((uint64_t)s1.y << 32) | s1.x) + gq;
-                g0 = __ldg(reinterpret_cast<const uint4 *>(src));
-                g1 = __ldg(reinterpret_cast<const uint4 *>(src + 16));
-                if (gq + UN_GRP < ((e_rel + 31u) & ~31u)) g2 = __ldg(reinterpret_cast<const uint32_t *>(src + 32));
-            }
-            sts128v(entry_sa, g0.x, g0.y, g0.z, g0.w);
-            sts128v(entry_sa + 16, g1.x, g1.y, g1.z, g1.w);
-            sts64v(entry_sa + 32, g2, 0u);
-            sts32v(entry_sa + 40, t.x);
-        }
+        sts32v(entry_sa + 40, t.x); // (phase 2 reaches the event's text beyond its 40 bytes through this)
         // Re-run the filter over the quarters that reported (usually one), one byte per update, this time recording
         // which start positions fired and which bytes are NUL.  Quarter k: bytes 8k..8k+11 -- three bytes of run-in,
         // then the starts 8k..8k+8 report at the bytes 8k+3..8k+11, and so do the NULs among the bytes 8k..8k+8 (the
@@ -594,8 +622,8 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
     }
     // publish what phase 2 needs next to the event's bytes
     if (lane < n) {
-        sts32v(entry_sa + 36, nextb);
-        sts32v(entry_sa + 44, bm); // over the quarter reports
+        sts8v(d.scratch_sa + SC_NEXTB + lane, nextb);
+        sts32v(entry_sa + 44, bm);
     }
     // alive candidates, numbered across the lanes
     const uint32_t cnt = __popc(am);
@@ -631,7 +659,7 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
             for (uint32_t j = first; j < t; j++) m &= m - 1;
             const uint32_t i = __ffs(m) - 1;
             const uint32_t owner_sa = t_sa + l * UN_T_BYTES1;
-            const uint32_t onext = lds32v(owner_sa + 36), obm = lds32v(owner_sa + 44);
+            const uint32_t onext = lds8v(d.scratch_sa + SC_NEXTB + l), obm = lds32v(owner_sa + 44);
             const uint32_t above = obm & ~((2u << i) - 1u); // packet starts after byte i
             const uint32_t room = (above ? (uint32_t)__ffs(above) - 1u : onext) - i;
             if (d.vtab_sa) verify_start<true>(d, pc, owner_sa, i, room);
@@ -643,7 +671,11 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
 
 // the same out of line, for the places that are not in the row loop (taking an item, the end of the batch): a call in
 // the row loop itself would cost that loop five spilled registers (the callee's needs bind at every call site)
-__device__ __noinline__ void drain_events(const uint32_t head, const uint32_t n) { drain_body(head, n); }
+__device__ __noinline__ void drain_events(const uint32_t head, const uint32_t n)
+{
+    drain_fetch(head, n);
+    drain_body(head, n);
+}
 
 // NUL-dense row.  An event without candidates exists only to tell later candidates where the last NUL before them
 // is; when the next event of the row is of the same kind, that one tells them a later NUL and this one is not needed:
@@ -707,7 +739,9 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     // warp sees in a launch) and an address is ring + (state >> 22); the oldest pending event sits `pending` slots
     // before the next one.
     static_assert(UN_QCAP * UN_Q_BYTES1 == 1024, "the ring offset lives in the top 10 bits of qs");
-    constexpr uint32_t QS_SLOT = UN_Q_BYTES1 << 22, QS_PENDING = (1u << 22) - 1u;
+    static_assert(UN_QCAP == 128 && 2 * UN_QDRAIN + 2 * 32 <= UN_QCAP, "pending events fit 7 bits and the ring");
+    // bit 8: the text of the 32 oldest events is on its way into the staging slots (drain_fetch was issued)
+    constexpr uint32_t QS_SLOT = UN_Q_BYTES1 << 22, QS_PENDING = 0xffu, QS_FETCHED = 0x100u;
     uint32_t qs = 0;
     auto pending = [&]() -> uint32_t { return qs & QS_PENDING; };
     auto oldest = [&]() -> uint32_t { return ((qs >> 22) / UN_Q_BYTES1 - pending()) & (UN_QCAP - 1); };
@@ -869,16 +903,22 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         };
 #pragma unroll 1
         for (;;) {
-            // With the loads of the next two rows on their way: resolve 32 events while there are that many -- here and
-            // nowhere else in the loop, inlined (one copy of the code, and no call whose register needs the loop would
-            // have to respect).
-            while (pending() >= UN_QDRAIN) {
+            // With the loads of the next two rows on their way: resolve the 32 oldest events if their text was asked
+            // for a trip ago (or if the ring would not take two more rows otherwise) -- here and nowhere else in the
+            // loop, inlined (one copy of the code, and no call whose register needs the loop would have to respect).
+            while ((qs & QS_FETCHED) || pending() >= 2 * UN_QDRAIN) {
+                if (!(qs & QS_FETCHED)) drain_fetch(oldest(), UN_QDRAIN);
                 drain_body(oldest(), UN_QDRAIN);
-                qs -= UN_QDRAIN;
+                qs = (qs & ~QS_FETCHED) - UN_QDRAIN;
                 if (lane == 0) { // that many fewer events of older items
                     const uint32_t older = lds32v(warp_scratch_sa() + SC_STATE + 4);
                     sts32v(warp_scratch_sa() + SC_STATE + 4, older > UN_QDRAIN ? older - UN_QDRAIN : 0u);
                 }
+            }
+            // 32 or more pending: their text starts its way from L2 now and is resolved at the top of the next trip
+            if (pending() >= UN_QDRAIN) {
+                drain_fetch(oldest(), UN_QDRAIN);
+                qs |= QS_FETCHED;
             }
             scan_row(b0);
             if (advance()) break;
@@ -893,6 +933,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
             if (advance()) break;
 #endif
         }
+        qs &= ~QS_FETCHED; // whoever resolves those events next asks for their text again
     }
     // leftovers
     while (pending()) resolve_oldest();
