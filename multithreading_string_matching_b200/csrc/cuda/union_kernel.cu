@@ -133,6 +133,8 @@ struct union_params {
     uint32_t vt_slots_a, vt_shift_a, vt_slots_b, vt_shift_b, vt_one, vt_rec, vt_blob;
     uint32_t mul64, mul4096; // the values 64 and 4096, passed at run time so that the shift-ors compile to integer
                              // multiply-adds on the FMA pipe instead of competing for the ALU pipe
+    uint32_t sel[4];         // 0x80 << 8k: the IDP.4A's byte selectors, read from the constant bank by the instruction
+                             // itself (as immediates they cost the row loop four UMOVs per row)
     unsigned long long *uniq_counts;
     // fused expansion + reduction (n_out > 0): the last block to finish adds every pattern's count, in file
     // order, to out[0..n_out) -- this GPU's count vector and/or its peers' (NVLink-mapped)
@@ -193,16 +195,14 @@ __global__ void kmpb_union_partition_kernel(const uint64_t *__restrict__ offsets
 struct row_regs {
     uint32_t w[8];
 };
-// 32 bytes global -> registers in one instruction (SASS LDG.E.256, sm_100), L1 not allocated (the row is used once),
-// under a predicate; a lane that does not load keeps what its registers held (an older row of the same item,
-// or zeros): whatever it reports from them lies past the item's end and is cut by the resolve step
-template <uint32_t OFF>
-__device__ __forceinline__ void ldg256_if(bool on, row_regs &b, const void *src)
+// 32 bytes global -> registers in one instruction (SASS LDG.E.256, sm_100), L1 not allocated (the row is used once).
+// Unconditional, into pure outputs: a predicated load has to keep the registers' old values, and ptxas then loads
+// into temporaries and moves (eight moves per row) once the load sits in the middle of another row's scan.
+__device__ __forceinline__ void ldg256(row_regs &b, const void *src)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
-                 "@p ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+%10];\n\t}"
-                 : "+r"(b.w[0]), "+r"(b.w[1]), "+r"(b.w[2]), "+r"(b.w[3]), "+r"(b.w[4]), "+r"(b.w[5]), "+r"(b.w[6]), "+r"(b.w[7])
-                 : "l"(src), "r"((uint32_t)on), "n"(OFF));
+    asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]), "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7])
+                 : "l"(src));
 }
 // 4 bytes under a predicate (lane 31's lookahead); 0 otherwise
 __device__ __forceinline__ uint32_t ldg32_if(bool on, const void *src)
@@ -318,8 +318,9 @@ __device__ __forceinline__ uint32_t clamp32(int32_t x) { return (uint32_t)min(ma
 
 // filter words of byte k (0..3) of `word`: the IDP.4A builds the whole shared address, byte * 128 + the lane's base
 // in table L (lutL) or G (lutG)
-#define LUT_L(word, k) lds32(__dp4a((uint32_t)(word), 0x80u << (8 * (k)), lutL))
-#define LUT_G(word, k) lds32_g(__dp4a((uint32_t)(word), 0x80u << (8 * (k)), lutL))
+#define LUT_L(word, k) lds32(__dp4a((uint32_t)(word), DP_SEL(k), lutL))
+#define LUT_G(word, k) lds32_g(__dp4a((uint32_t)(word), DP_SEL(k), lutL))
+#define DP_SEL(k) (0x80u << (8 * (k))) // 128 x byte k
 // one two-byte update: bytes k0, k1 = k0 + 1 of `word`
 #define SA2(word, k0) (S = (S * mul2 + 4095u) & LUT_G(word, k0) & LUT_L(word, (k0) + 1))
 // one one-byte update (the resolve step's re-run)
@@ -693,6 +694,8 @@ __device__ __noinline__ uint32_t drop_superseded(uint32_t tops, const uint32_t m
 // warp-uniform value, in a form the compiler can keep in a uniform register
 __device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(FULL, v, 0); }
 __device__ __forceinline__ uint64_t uni(uint64_t v) { return __shfl_sync(FULL, v, 0); }
+#undef DP_SEL
+#define DP_SEL(k) p.sel[k]
 __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_constant__ union_params p)
 {
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem);                      // L, then G
@@ -802,19 +805,19 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         uint32_t gcur = lane | par << 31;
 
         // The row `ahead` rows after the one being scanned, global -> registers: every lane its own 32 bytes with one
-        // 256-bit load.  Rows past the item's end and the lanes past load_end in its last row load nothing and keep
-        // what they held: whatever they report from it is cut to the item's byte range by the resolve step.  The L2
+        // 256-bit load.  A lane whose group lies past what the item lets it load (rows past the item's end, the lanes
+        // past load_end in its last row) loads the item's last group instead (src + left is load_end, whichever row
+        // src is in): whatever it reports from that is cut to the item's byte range by the resolve step.  The L2
         // prefetch of the row UN_PF rows further on rides on the same address.
         auto load_row = [&](auto ahead_c, row_regs &b) {
             constexpr uint32_t ahead = decltype(ahead_c)::value;
-            const int32_t l = left - (int32_t)(ahead * UN_ROW);
-            ldg256_if<ahead * UN_ROW>(l > 0, b, src);
-            if (UN_PF) prefetch_l2_if<(ahead + UN_PF) * UN_ROW>(l > (int32_t)(UN_PF * UN_ROW), src);
+            ldg256(b, src + (ptrdiff_t)min((int32_t)(ahead * UN_ROW), left - (int32_t)UN_GRP));
+            if (UN_PF) prefetch_l2_if<(ahead + UN_PF) * UN_ROW>(left > (int32_t)((ahead + UN_PF) * UN_ROW), src);
         };
 
         // one row: filter its bytes, append the events, refill the buffer with the row UN_NBUF ahead, and resolve
         // 32 events once the list holds that many
-        auto scan_row = [&](row_regs &b) {
+        auto scan_row = [&](row_regs &b, row_regs &freed) {
             // the 4 bytes after my group: the next lane's first word; for lane 31 the first word of the next row, asked
             // for now (the row's own load is already on its way, so it comes from L2 or rides on that fill) and used last
             uint32_t la;
@@ -824,6 +827,11 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                          "@q ld.global.L1::no_allocate.u32 %0, [%3+32];\n\t}"
                          : "=&r"(la)
                          : "r"(b.w[0]), "r"(left), "l"(src));
+            // The buffer scanned before this one is free: the row UN_NBUF - 1 ahead goes into it -- NOW, after this row's
+            // first use has waited for its own load, not at the end of the previous scan: ptxas tracks all the row loads
+            // with one scoreboard, and a wait on it waits for every load issued so far (the first use of each row used
+            // to wait for the load issued a few instructions before it: no prefetch distance at all).
+            load_row(std::integral_constant<uint32_t, UN_NBUF - 1>{}, freed);
 
             // ---- shift-and filter over 36 bytes, two per update ---------------------------------------
             // Update j takes bytes 2j, 2j+1 and reports what starts at 2j-3 (bits 24..29) and 2j-2 (bits 18..23): the
@@ -874,24 +882,22 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                 }
                 qs += n * (QS_SLOT + 1u);
             }
-            // the buffer is free: the row UN_NBUF ahead goes into it
-            load_row(std::integral_constant<uint32_t, UN_NBUF>{}, b);
         };
 
         // the first UN_PF rows' lines: 128 bytes per lane and step
         if (UN_PF)
             for (uint32_t x = lane * 128u; x < UN_PF * UN_ROW; x += 4096u) prefetch_l2_if(x < load_end, src - lane * UN_GRP + x);
         // UN_NBUF rows per trip: the buffers are compile-time registers, no moves between them
+        // (the last buffer gets its first row from the first scan)
         row_regs b0 = {}, b1 = {};
         load_row(std::integral_constant<uint32_t, 0>{}, b0);
-        load_row(std::integral_constant<uint32_t, 1>{}, b1);
 #if KMPB_UN_NBUF >= 3
         row_regs b2 = {};
-        load_row(std::integral_constant<uint32_t, 2>{}, b2);
+        load_row(std::integral_constant<uint32_t, 1>{}, b1);
 #endif
 #if KMPB_UN_NBUF >= 4
         row_regs b3 = {};
-        load_row(std::integral_constant<uint32_t, 3>{}, b3);
+        load_row(std::integral_constant<uint32_t, 2>{}, b2);
 #endif
         // next row; the item is through when lane 0 has nothing left (its rows start at multiples of 32)
         auto advance = [&]() -> bool {
@@ -920,16 +926,26 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
                 drain_fetch(oldest(), UN_QDRAIN);
                 qs |= QS_FETCHED;
             }
-            scan_row(b0);
+#if KMPB_UN_NBUF == 2
+            scan_row(b0, b1);
             if (advance()) break;
-            scan_row(b1);
+            scan_row(b1, b0);
             if (advance()) break;
-#if KMPB_UN_NBUF >= 3
-            scan_row(b2);
+#elif KMPB_UN_NBUF == 3
+            scan_row(b0, b2);
             if (advance()) break;
-#endif
-#if KMPB_UN_NBUF >= 4
-            scan_row(b3);
+            scan_row(b1, b0);
+            if (advance()) break;
+            scan_row(b2, b1);
+            if (advance()) break;
+#else
+            scan_row(b0, b3);
+            if (advance()) break;
+            scan_row(b1, b0);
+            if (advance()) break;
+            scan_row(b2, b1);
+            if (advance()) break;
+            scan_row(b3, b2);
             if (advance()) break;
 #endif
         }
@@ -1037,6 +1053,7 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     p.vt_one = h.vtab[5]; p.vt_rec = h.vtab[6]; p.vt_blob = h.vtab[7];
     p.mul64 = 64u;
     p.mul4096 = 4096u;
+    for (int k = 0; k < 4; k++) p.sel[k] = 0x80u << (8 * k);
     p.uniq_counts = (unsigned long long *)d_uniq_counts;
     p.pat_to_uniq = ctx->dev.pat_to_uniq;
     p.n_pat = h.n_pat;
