@@ -327,7 +327,8 @@ def reference_arm(args, patterns):
     if rank != 0:
         return
     ref = CpuReference(patterns, args.payload_len)
-    n = args.ref_packets or ref.calibrate(8.0)
+    # each step a bounded sample, sized so that the whole --steps K --warmup W run ends within about two minutes
+    n = args.ref_packets or ref.calibrate(max(1.0, min(8.0, 120.0 / max(args.warmup + args.steps, 1))))
     if args.ref_packets:
         ref.prepare(n)
     times = []
