@@ -101,10 +101,14 @@ constexpr uint32_t FULL = 0xffffffffu;
 // they fit), the probe tables (if they fit).
 constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_BYTES1;
 constexpr uint32_t UN_T_BYTES = UN_WARPS * UN_QDRAIN * UN_T_BYTES1; // the 32 events a warp is resolving, with their text
+constexpr uint32_t UN_CCAP = 64;      // slots of a warp's candidate ring: fewer than 32 waiting + at most one per lane on top
+constexpr uint32_t UN_C_BYTES1 = 16;  // a candidate: its first 8 text bytes, its absolute position, the bytes left in its packet
+constexpr uint32_t UN_C_BYTES = UN_WARPS * UN_CCAP * UN_C_BYTES1;
 constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
 constexpr uint32_t UN_OFF_Q = 2 * UN_LUT_BYTES;
 constexpr uint32_t UN_OFF_T = UN_OFF_Q + UN_Q_BYTES;
-constexpr uint32_t UN_OFF_SCRATCH = UN_OFF_T + UN_T_BYTES;
+constexpr uint32_t UN_OFF_C = UN_OFF_T + UN_T_BYTES;       // the warps' candidate rings
+constexpr uint32_t UN_OFF_SCRATCH = UN_OFF_C + UN_C_BYTES;
 constexpr uint32_t UN_OFF_MISC = UN_OFF_SCRATCH + UN_SCRATCH_BYTES; // 128 bytes: what the resolve step reads of the
                                                                     // launch parameters (DC_*), the "last block" flag
 constexpr uint32_t UN_OFF_COUNTS = UN_OFF_MISC + 128;
@@ -343,8 +347,8 @@ enum { DC_TEXT_LO = 0, DC_TEXT_HI,   // p.bytes - p.abs_base: absolute byte 0
 //   NUL byte among its events resolved so far (0: none), and either 0x80000000 | L when all its packets have L bytes or
 //   (ke - ks) / (e_rel - b_rel) as a float (the interpolation guess of the packet lookup) --
 // then, at byte 64, {parity of the item being scanned, how many of the pending events belong to items before it}, and at
-// byte 72 one byte per event being resolved: where the first packet boundary at or after the end of its group lies.
-constexpr uint32_t SC_STATE = 64, SC_NEXTB = 72;
+// byte 72 the state of the warp's candidate ring.
+constexpr uint32_t SC_STATE = 64, SC_CAND = 72;
 
 extern __shared__ __align__(1024) uint8_t smem[];
 // shared address of the dynamic shared memory (uniform registers; the generic-to-shared conversion costs more)
@@ -379,35 +383,30 @@ __device__ __forceinline__ void count_hit(const drain_args &d, uint32_t u)
     else atomicAdd(reinterpret_cast<unsigned long long *>(const_cast<uint8_t *>(dc_ptr(DC_CNT_LO))) + u, 1ull);
 }
 
-// 4 text bytes starting at byte `pos` of the event at entry_sa, of which the first `need` (>= 1) matter: from
-// the event while its 40 bytes last, then from global memory (never past the word that holds the last
-// needed byte, which lies inside the packet).  Where the event's group lies in global memory follows from its
-// group index and its item's row0 in the warp's scratch words.
-__device__ __forceinline__ uint32_t text_window(const drain_args &d, uint32_t entry_sa, uint32_t pos, uint32_t need)
+// 4 text bytes starting at g, of which the first `need` (>= 1) matter: never read past the word that holds the last
+// needed byte, which lies inside the packet.
+__device__ __forceinline__ uint32_t text_window(const uint8_t *g, uint32_t need)
 {
-    if (pos + 4 <= 40) {
-        const uint32_t a = entry_sa + (pos & ~3u);
-        return __funnelshift_r(lds32v(a), lds32v(a + 4), 8u * (pos & 3u));
-    }
-    const uint32_t meta = lds32v(entry_sa + 40);
-    const uint2 r0 = lds64v(d.scratch_sa + ((meta >> 31) << 5) + 16);
-    const uint8_t *gw = dc_ptr(DC_TEXT_LO) + (((uint64_t)r0.y << 32) | r0.x) + ((meta & 0x7fffffffu) << 5) + (pos & ~3u);
-    const uint32_t lo = __ldg(reinterpret_cast<const uint32_t *>(gw));
-    const uint32_t hi = (pos & 3u) + (need < 4 ? need : 4u) > 4u ? __ldg(reinterpret_cast<const uint32_t *>(gw) + 1) : 0u;
-    return __funnelshift_r(lo, hi, 8u * (pos & 3u));
+    const uint32_t sh = (uint32_t)reinterpret_cast<uintptr_t>(g) & 3u;
+    const uint32_t *gw = reinterpret_cast<const uint32_t *>(g - sh);
+    const uint32_t lo = __ldg(gw);
+    const uint32_t hi = sh + (need < 4 ? need : 4u) > 4u ? __ldg(gw + 1) : 0u;
+    return __funnelshift_r(lo, hi, 8u * sh);
 }
 
-// Every pattern that starts at byte `i` (0..31) of the event at entry_sa and is at most `room` (>= 1) bytes long
-// is counted.  The candidate's first two bytes select one slot of probe table A (the two-byte patterns), its first
-// three one slot of table B (the longer ones); the slots' records carry the pattern's first 8 bytes and their masks,
-// so a record costs one 16-byte load and one masked compare, and only a record that agrees on those bytes is looked
-// at further.
 // where the probe tables' parts are, read once per resolve step
 struct probe_consts {
     uint32_t slots_a, shift_a, slots_b, shift_b, one, rec;
 };
+// A candidate: text bytes 0..3 (x0) and 4..7 (x1) from its start, `room` (>= 1) = bytes from its start to the end of its
+// packet, pos = its absolute position.  Every pattern that starts there and is at most `room` bytes long is counted.
+// The candidate's first two bytes select one slot of probe table A (the two-byte patterns), its first three one slot of
+// table B (the longer ones); the slots' records carry the pattern's first 8 bytes and their masks, so a record costs one
+// 16-byte load and one masked compare, and only a record that agrees on those bytes is looked at further (patterns of
+// more than 8 bytes: word by word against the text in global memory -- L2, the row was read a moment ago).
 template <bool VS>
-__device__ __forceinline__ void verify_start(const drain_args &d, const probe_consts &pc, uint32_t entry_sa, uint32_t i, uint32_t room)
+__device__ __forceinline__ void verify_cand(const drain_args &d, const probe_consts &pc, const uint32_t x0, const uint32_t x1,
+                                            const uint32_t room, const uint64_t pos)
 {
     const uint32_t *vtab_g = VS ? nullptr : reinterpret_cast<const uint32_t *>(dc_ptr(DC_VTAB_LO));
     auto vt = [&](uint32_t word) -> uint32_t { return VS ? lds32(d.vtab_sa + 4u * word) : __ldg(vtab_g + word); };
@@ -418,8 +417,6 @@ __device__ __forceinline__ void verify_start(const drain_args &d, const probe_co
         return VS ? lds64(d.vtab_sa + 4u * word) : __ldg(reinterpret_cast<const uint2 *>(vtab_g + word));
     };
     const uint32_t vt_one = pc.one, vt_slots_a = pc.slots_a, vt_slots_b = pc.slots_b;
-    // text bytes i..i+3 and, if a pattern that long fits at all, i+4..i+7 (both inside the event's 40 bytes)
-    const uint32_t x0 = __funnelshift_r(lds32v(entry_sa + (i & ~3u)), lds32v(entry_sa + (i & ~3u) + 4), 8u * (i & 3u));
     if (vt_one) { // one-byte patterns: a direct table (room >= 1 always holds)
         const uint32_t u = vt(vt_one + (x0 & 0xffu));
         if (u != 0xffffffffu) count_hit(d, u);
@@ -430,7 +427,6 @@ __device__ __forceinline__ void verify_start(const drain_args &d, const probe_co
     if (vt_slots_b && room >= 3) eb = vt2(vt_slots_b + 2u * (((x0 & 0xffffffu) * 0x9e3779b1u) >> pc.shift_b));
     const uint32_t nrec = ea.y + eb.y;
     if (nrec == 0) return; // most candidates end here: no pattern begins with these bytes
-    const uint32_t x1 = room > 4 ? text_window(d, entry_sa, i + 4, room - 4) : 0u;
     const uint32_t vt_rec = pc.rec;
     for (uint32_t j = 0; j < nrec; j++) {
         const uint32_t r = vt_rec + 8u * (j < ea.y ? ea.x + j : eb.x + (j - ea.y));
@@ -444,14 +440,51 @@ __device__ __forceinline__ void verify_start(const drain_args &d, const probe_co
         bool same = true;
         if (m > 8) {
             const uint32_t pw0 = dc(DC_BLOB) + vt(r + 6);
-            for (uint32_t jj = 8; jj < m && same; jj += 4) { // pattern bytes jj..jj+3 against text bytes i+jj..
+            const uint8_t *g = dc_ptr(DC_TEXT_LO) + pos;
+            for (uint32_t jj = 8; jj < m && same; jj += 4) { // pattern bytes jj..jj+3 against text bytes jj..
                 const uint32_t pw = vt(pw0 + (jj >> 2)), rem = m - jj;
-                const uint32_t diff = text_window(d, entry_sa, i + jj, rem) ^ pw;
+                const uint32_t diff = text_window(g + jj, rem) ^ pw;
                 same = (rem >= 4 ? diff : diff & ((1u << (8 * rem)) - 1u)) == 0;
             }
         }
         if (same) count_hit(d, b.y);
     }
+}
+
+// The warp's candidate ring: what phase 1 of the resolve steps found alive waits here until 32 have come together, so
+// that phase 2 always runs with every lane busy (the candidates of one resolve step seldom fill a whole number of
+// rounds).  A slot: {x0, x1, position low word, room | position high bits << 8}.  State word (scratch, SC_CAND):
+// waiting candidates | slot the next one goes to << 8.
+__device__ __forceinline__ uint32_t warp_c_sa() { return smem_sa() + UN_OFF_C + (threadIdx.x >> 5) * (UN_CCAP * UN_C_BYTES1); }
+// verify the n (<= 32) oldest of `waiting` candidates, one per lane
+__device__ __forceinline__ void verify_round(const drain_args &d, const uint32_t next_slot, const uint32_t waiting, const uint32_t n)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane < n) {
+        probe_consts pc;
+        const uint4 c0 = lds128(smem_sa() + UN_OFF_MISC + 4u * DC_SLOTS_A);
+        const uint2 c1 = lds64(smem_sa() + UN_OFF_MISC + 4u * DC_ONE);
+        pc.slots_a = c0.x; pc.shift_a = c0.y; pc.slots_b = c0.z; pc.shift_b = c0.w; pc.one = c1.x; pc.rec = c1.y;
+        const uint4 e = lds128v(warp_c_sa() + ((next_slot - waiting + lane) & (UN_CCAP - 1)) * UN_C_BYTES1);
+        const uint64_t pos = ((uint64_t)(e.w >> 8) << 32) | e.z;
+        if (d.vtab_sa) verify_cand<true>(d, pc, e.x, e.y, e.w & 0xffu, pos);
+        else verify_cand<false>(d, pc, e.x, e.y, e.w & 0xffu, pos);
+    }
+}
+// the candidates still waiting at the end of a batch
+__device__ __noinline__ void flush_candidates()
+{
+    drain_args d;
+    d.q_sa = warp_q_sa();
+    d.scratch_sa = warp_scratch_sa();
+    d.vtab_sa = dc(DC_VTAB_SA);
+    d.counts_sa = dc(DC_COUNTS_SA);
+    __syncwarp();
+    const uint32_t cs = lds32v(d.scratch_sa + SC_CAND);
+    verify_round(d, cs >> 8, cs & 0xffu, cs & 0xffu); // fewer than 32 are waiting between resolve steps
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) sts32v(d.scratch_sa + SC_CAND, cs & ~0xffu);
+    __syncwarp();
 }
 
 // Phase 0 of a resolve step, on its own so that the row loop can issue it a row or two ahead: the n (<= 32) oldest
@@ -482,7 +515,8 @@ __device__ __forceinline__ void drain_fetch(const uint32_t head, const uint32_t 
 // Phase 1, one event per lane: which start positions of the event's quarter(s) fired, where the NULs are, which
 // packet(s) they lie in -> mask of candidate starts that are alive (inside the item, no NUL before them in their
 // packet) and mask of packet boundaries inside the group.
-// Phase 2, every lane its own alive candidates: probe, compare, count.
+// Phase 2: the alive candidates go to the warp's candidate ring; every 32 of them are verified, one per lane: probe,
+// compare, count.
 //
 // The events belong to the work item the warp is scanning or to the one before it (the row loop sees to that); an
 // event carries its item's parity, and what the resolve step has to know about either item waits in the warp's
@@ -504,7 +538,7 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
     const uint32_t t_sa = warp_t_sa();
     const uint32_t entry_sa = t_sa + lane * UN_T_BYTES1; // my event's slot among the 32 being resolved
     uint32_t cm = 0, zm = 0, gq = 0, par = 0;
-    uint32_t ks = 0, ke = 0, b_rel = 0, e_rel = 0, row0_lo = 0, carry = 0, psize = 0;
+    uint32_t ks = 0, ke = 0, b_rel = 0, e_rel = 0, row0_lo = 0, row0_hi = 0, carry = 0, psize = 0;
     if (lane < n) {
         const uint2 t = lds64v(d.q_sa + ((head + lane) & (UN_QCAP - 1)) * UN_Q_BYTES1); // group index (relative to row0) | item parity << 31, quarter reports
         par = t.x >> 31;
@@ -512,8 +546,7 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
         const uint32_t set_sa = d.scratch_sa + (par << 5); // my item's scratch set
         const uint4 s0 = lds128v(set_sa), s1 = lds128v(set_sa + 16);
         ks = s0.x; ke = s0.y; b_rel = s0.z; e_rel = s0.w;
-        row0_lo = s1.x; carry = s1.z; psize = s1.w;
-        sts32v(entry_sa + 40, t.x); // (phase 2 reaches the event's text beyond its 40 bytes through this)
+        row0_lo = s1.x; row0_hi = s1.y; carry = s1.z; psize = s1.w;
         // Re-run the filter over the quarters that reported (usually one), one byte per update, this time recording
         // which start positions fired and which bytes are NUL.  Quarter k: bytes 8k..8k+11 -- three bytes of run-in,
         // then the starts 8k..8k+8 report at the bytes 8k+3..8k+11, and so do the NULs among the bytes 8k..8k+8 (the
@@ -621,52 +654,35 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
         }
         nextb = pe - gq > 255 ? 255u : pe - gq;
     }
-    // publish what phase 2 needs next to the event's bytes
-    if (lane < n) {
-        sts8v(d.scratch_sa + SC_NEXTB + lane, nextb);
-        sts32v(entry_sa + 44, bm);
-    }
-    // alive candidates, numbered across the lanes
-    const uint32_t cnt = __popc(am);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (uint32_t dd = 1; dd < 32; dd <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, incl, dd);
-        if (lane >= dd) incl += v;
-    }
-    const uint32_t total = __shfl_sync(FULL, incl, 31);
-    const uint32_t excl = incl - cnt;
-    __syncwarp();
-    // one alive candidate per lane, whichever event it belongs to
-    probe_consts pc;
-    {
-        const uint4 c0 = lds128(smem_sa() + UN_OFF_MISC + 4u * DC_SLOTS_A);
-        const uint2 c1 = lds64(smem_sa() + UN_OFF_MISC + 4u * DC_ONE);
-        pc.slots_a = c0.x; pc.shift_a = c0.y; pc.slots_b = c0.z; pc.shift_b = c0.w; pc.one = c1.x; pc.rec = c1.y;
-    }
-    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-        const uint32_t t = t0 + lane;
-        // owner of candidate t: the first lane whose inclusive count exceeds t
-        uint32_t l = 0;
-#pragma unroll
-        for (uint32_t st = 16; st; st >>= 1) {
-            const uint32_t v = __shfl_sync(FULL, incl, l + st - 1);
-            if (v <= t) l += st;
+    // Phase 2.  Every lane appends its alive candidates to the warp's candidate ring, one per trip, and whenever 32 are
+    // waiting they are verified, one per lane -- whichever event they came from, this resolve step's or an earlier one's.
+    // (A candidate is self-contained: its first 8 bytes, its position, the bytes left in its packet.)
+    const uint64_t gpos = (((uint64_t)row0_hi << 32) | row0_lo) + gq; // absolute position of my group (a multiple of 32)
+    uint32_t cs = lds32v(d.scratch_sa + SC_CAND);                     // waiting | next slot << 8
+    const uint32_t c_sa = warp_c_sa();
+    for (;;) {
+        const uint32_t any = __ballot_sync(FULL, am != 0);
+        if (any == 0) break;
+        if (am) {
+            const uint32_t i = __ffs(am) - 1;
+            am &= am - 1;
+            const uint32_t a = entry_sa + (i & ~3u), sh = 8u * (i & 3u);
+            const uint32_t w0 = lds32v(a), w1 = lds32v(a + 4), w2 = lds32v(a + 8); // i + 7 < 40: inside the event's text
+            const uint32_t above = bm & ~((2u << i) - 1u);                          // packet starts after byte i
+            const uint32_t room = (above ? (uint32_t)__ffs(above) - 1u : nextb) - i;
+            const uint32_t slot = ((cs >> 8) + __popc(any & lt)) & (UN_CCAP - 1);
+            sts128v(c_sa + slot * UN_C_BYTES1, __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                    (uint32_t)gpos | i, room | ((uint32_t)(gpos >> 32) << 8));
         }
-        l &= 31;
-        uint32_t m = __shfl_sync(FULL, am, l);
-        const uint32_t first = __shfl_sync(FULL, excl, l);
-        if (t < total) {
-            for (uint32_t j = first; j < t; j++) m &= m - 1;
-            const uint32_t i = __ffs(m) - 1;
-            const uint32_t owner_sa = t_sa + l * UN_T_BYTES1;
-            const uint32_t onext = lds8v(d.scratch_sa + SC_NEXTB + l), obm = lds32v(owner_sa + 44);
-            const uint32_t above = obm & ~((2u << i) - 1u); // packet starts after byte i
-            const uint32_t room = (above ? (uint32_t)__ffs(above) - 1u : onext) - i;
-            if (d.vtab_sa) verify_start<true>(d, pc, owner_sa, i, room);
-            else verify_start<false>(d, pc, owner_sa, i, room);
+        cs += __popc(any) * 0x101u;
+        __syncwarp();
+        if ((cs & 0xffu) >= 32u) {
+            verify_round(d, cs >> 8, cs & 0xffu, 32u);
+            cs -= 32u;
+            __syncwarp();
         }
     }
+    if (lane == 0) sts32v(d.scratch_sa + SC_CAND, cs);
     __syncwarp();
 }
 
@@ -953,6 +969,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
     }
     // leftovers
     while (pending()) resolve_oldest();
+    flush_candidates();
 
     __syncthreads();
     if (p.counts_in_smem)
