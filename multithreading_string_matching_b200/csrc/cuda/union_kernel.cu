@@ -327,8 +327,6 @@ __device__ __forceinline__ uint32_t clamp32(int32_t x) { return (uint32_t)min(ma
 #define DP_SEL(k) (0x80u << (8 * (k))) // 128 x byte k
 // one two-byte update: bytes k0, k1 = k0 + 1 of `word`
 #define SA2(word, k0) (S = (S * mul2 + 4095u) & LUT_G(word, k0) & LUT_L(word, (k0) + 1))
-// one one-byte update (the resolve step's re-run)
-#define SA1(word, k) (S = (S * mul1 + 63u) & LUT_L(word, k))
 
 // The launch parameters the resolve step reads, copied to shared memory once per block (word indices in the block at
 // UN_OFF_MISC): a function that is not inlined would reach the kernel's parameter space through generic loads.
@@ -337,7 +335,7 @@ enum { DC_TEXT_LO = 0, DC_TEXT_HI,   // p.bytes - p.abs_base: absolute byte 0
        DC_VTAB_LO, DC_VTAB_HI,   // p.vtab (global)
        DC_CNT_LO, DC_CNT_HI,     // p.uniq_counts
        DC_SLOTS_A, DC_SHIFT_A, DC_SLOTS_B, DC_SHIFT_B, DC_ONE, DC_REC, DC_BLOB,
-       DC_MUL64, DC_VTAB_SA,     // shared address of the probe tables, 0 = they are in global memory
+       DC_MUL4096, DC_VTAB_SA,     // shared address of the probe tables, 0 = they are in global memory
        DC_COUNTS_SA,             // shared address of the counters, 0 = global atomics
        DC_LAST = 31 };           // "I am the last block" flag
 
@@ -530,7 +528,7 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
     d.vtab_sa = dc(DC_VTAB_SA);
     d.counts_sa = dc(DC_COUNTS_SA);
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t lutL = smem_sa() + (lane << 2), mul1 = dc(DC_MUL64);
+    const uint32_t lutL = smem_sa() + (lane << 2), mul2 = dc(DC_MUL4096);
     uint32_t lt;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
     cp_async_wait_all(); // phase 0 (drain_fetch): my event's bytes are in its slot
@@ -557,17 +555,21 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
             quarters &= quarters - 1;
             const uint32_t w0 = lds32v(entry_sa + k8), w1 = lds32v(entry_sa + k8 + 4), w2 = lds32v(entry_sa + k8 + 8);
             uint32_t S = 0, cmr = 0, zr = 0;
-#define SV1(word, k)                                                    \
-    do {                                                                \
-        SA1(word, k);                                                   \
-        zr = __funnelshift_l(S << 8, zr, 1);                            \
-        cmr = __funnelshift_l((S & 0x007c0000u) + 0x7ffc0000u, cmr, 1); \
+            // Two bytes per update, as in the row loop; after an update bits 24..28 / 18..22 hold the candidate buckets of
+            // the start three before b0 / b1, bits 29 / 23 "that byte is NUL".  Adding 0x1f to a 5-bit field carries into
+            // the bit above it iff the field is not zero, and x * 132 moves bits 29 and 23 of x to bits 31 and 30: two
+            // report bits per update and kind, shifted into cmr / zr from below (nothing can report before byte 3).
+#define SV2(word, k0)                                                                                           \
+    do {                                                                                                        \
+        SA2(word, k0);                                                                                          \
+        zr = __funnelshift_l((S & 0x20800000u) * 132u, zr, 2);                                                  \
+        cmr = __funnelshift_l((((S & 0x1f7c0000u) + 0x1f7c0000u) & 0x20800000u) * 132u, cmr, 2);               \
     } while (0)
-            SA1(w0, 0); SA1(w0, 1); SA1(w0, 2);
-            SV1(w0, 3);
-            SV1(w1, 0); SV1(w1, 1); SV1(w1, 2); SV1(w1, 3);
-            SV1(w2, 0); SV1(w2, 1); SV1(w2, 2); SV1(w2, 3);
-#undef SV1
+            SA2(w0, 0);
+            SV2(w0, 2);
+            SV2(w1, 0); SV2(w1, 2);
+            SV2(w2, 0); SV2(w2, 2);
+#undef SV2
             cm |= (__brev(cmr) >> 23) << k8; // the first report is the highest of the 9 bits
             zm |= (__brev(zr) >> 23) << k8;
         }
@@ -660,6 +662,8 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
     const uint64_t gpos = (((uint64_t)row0_hi << 32) | row0_lo) + gq; // absolute position of my group (a multiple of 32)
     uint32_t cs = lds32v(d.scratch_sa + SC_CAND);                     // waiting | next slot << 8
     const uint32_t c_sa = warp_c_sa();
+    const uint32_t gpos_lo = (uint32_t)gpos, gpos_hi8 = (uint32_t)(gpos >> 32) << 8;
+    const bool walls = __any_sync(FULL, bm != 0); // some group of this step holds a packet boundary (C3: one step in two)
     for (;;) {
         const uint32_t any = __ballot_sync(FULL, am != 0);
         if (any == 0) break;
@@ -668,11 +672,14 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
             am &= am - 1;
             const uint32_t a = entry_sa + (i & ~3u), sh = 8u * (i & 3u);
             const uint32_t w0 = lds32v(a), w1 = lds32v(a + 4), w2 = lds32v(a + 8); // i + 7 < 40: inside the event's text
-            const uint32_t above = bm & ~((2u << i) - 1u);                          // packet starts after byte i
-            const uint32_t room = (above ? (uint32_t)__ffs(above) - 1u : nextb) - i;
+            uint32_t end = nextb; // the end of the candidate's packet: the first packet start after byte i
+            if (walls) {
+                const uint32_t above = bm & ~((2u << i) - 1u);
+                if (above) end = (uint32_t)__ffs(above) - 1u;
+            }
             const uint32_t slot = ((cs >> 8) + __popc(any & lt)) & (UN_CCAP - 1);
             sts128v(c_sa + slot * UN_C_BYTES1, __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
-                    (uint32_t)gpos | i, room | ((uint32_t)(gpos >> 32) << 8));
+                    gpos_lo | i, (end - i) | gpos_hi8);
         }
         cs += __popc(any) * 0x101u;
         __syncwarp();
@@ -741,7 +748,7 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         s_misc[DC_SLOTS_A] = p.vt_slots_a; s_misc[DC_SHIFT_A] = p.vt_shift_a;
         s_misc[DC_SLOTS_B] = p.vt_slots_b; s_misc[DC_SHIFT_B] = p.vt_shift_b;
         s_misc[DC_ONE] = p.vt_one; s_misc[DC_REC] = p.vt_rec; s_misc[DC_BLOB] = p.vt_blob;
-        s_misc[DC_MUL64] = p.mul64;
+        s_misc[DC_MUL4096] = p.mul4096;
         s_misc[DC_VTAB_SA] = p.vtab_in_smem ? saddr_of(s_vtab) : 0u;
         s_misc[DC_COUNTS_SA] = p.counts_in_smem ? saddr_of(s_counts) : 0u;
     }
@@ -1020,6 +1027,8 @@ int kmpb_launch_union(kmpb_ctx *ctx, const kmpb_batch &b, int slot, uint64_t *d_
     if (b.n_packets >= (1ull << 31)) return kmpb_fail(KMPB_ELIMIT, "more than 2^31-1 packets in one batch");
     if ((b.abs_base & 511) || ((uintptr_t)b.d_bytes & 31))
         return kmpb_fail(KMPB_EINVAL, "payload buffer must be 32-byte aligned");
+    if (b.end_byte >= (1ull << 56)) // a candidate's absolute position travels in 56 bits
+        return kmpb_fail(KMPB_ELIMIT, "absolute stream offsets of 2^56 and more");
     if (b.end_byte - b.abs_base >= (1ull << 36))
         return kmpb_fail(KMPB_ELIMIT, "more than 64 GiB of payload in one batch");
     const uint64_t span = b.end_byte - b.first_byte;
