@@ -101,7 +101,7 @@ constexpr uint32_t FULL = 0xffffffffu;
 // they fit), the probe tables (if they fit).
 constexpr uint32_t UN_Q_BYTES = UN_WARPS * UN_QCAP * UN_Q_BYTES1;
 constexpr uint32_t UN_T_BYTES = UN_WARPS * UN_QDRAIN * UN_T_BYTES1; // the 32 events a warp is resolving, with their text
-constexpr uint32_t UN_CCAP = 64;      // slots of a warp's candidate ring: fewer than 32 waiting + at most one per lane on top
+constexpr uint32_t UN_CCAP = 128;     // slots of a warp's candidate ring: fewer than 32 waiting + what a resolve step finds (else: trips of 32)
 constexpr uint32_t UN_C_BYTES1 = 16;  // a candidate: its first 8 text bytes, its absolute position, the bytes left in its packet
 constexpr uint32_t UN_C_BYTES = UN_WARPS * UN_CCAP * UN_C_BYTES1;
 constexpr uint32_t UN_SCRATCH_BYTES = UN_WARPS * 128;
@@ -114,7 +114,7 @@ constexpr uint32_t UN_OFF_MISC = UN_OFF_SCRATCH + UN_SCRATCH_BYTES; // 128 bytes
 constexpr uint32_t UN_OFF_COUNTS = UN_OFF_MISC + 128;
 constexpr size_t UN_SMEM_FIXED = UN_OFF_COUNTS;
 constexpr size_t UN_SMEM_MAX = 227 * 1024; // opt-in shared memory of one block on sm_100
-static_assert(UN_SMEM_FIXED + 16384 <= UN_SMEM_MAX, "shared memory budget");
+static_assert(UN_SMEM_FIXED + 12288 <= UN_SMEM_MAX, "shared memory budget");
 
 // the filter's geometry (automaton.c kmpb_filter6_build): fields of 6 bits, bits 0..4 the pattern buckets, bit 5 the NUL
 // detector; after a two-byte update b0's reports sit in bits 24..29, b1's in bits 18..23
@@ -345,7 +345,7 @@ enum { DC_TEXT_LO = 0, DC_TEXT_HI,   // p.bytes - p.abs_base: absolute byte 0
 //   NUL byte among its events resolved so far (0: none), and either 0x80000000 | L when all its packets have L bytes or
 //   (ke - ks) / (e_rel - b_rel) as a float (the interpolation guess of the packet lookup) --
 // then, at byte 64, {parity of the item being scanned, how many of the pending events belong to items before it}, and at
-// byte 72 the state of the warp's candidate ring.
+// byte 72 the state of the warp's candidate ring (two words).
 constexpr uint32_t SC_STATE = 64, SC_CAND = 72;
 
 extern __shared__ __align__(1024) uint8_t smem[];
@@ -451,11 +451,11 @@ __device__ __forceinline__ void verify_cand(const drain_args &d, const probe_con
 
 // The warp's candidate ring: what phase 1 of the resolve steps found alive waits here until 32 have come together, so
 // that phase 2 always runs with every lane busy (the candidates of one resolve step seldom fill a whole number of
-// rounds).  A slot: {x0, x1, position low word, room | position high bits << 8}.  State word (scratch, SC_CAND):
-// waiting candidates | slot the next one goes to << 8.
+// rounds).  A slot: {x0, x1, position low word, room | position high bits << 8}.  State (scratch, SC_CAND): two
+// free-running counters, slots handed out and slots verified.
 __device__ __forceinline__ uint32_t warp_c_sa() { return smem_sa() + UN_OFF_C + (threadIdx.x >> 5) * (UN_CCAP * UN_C_BYTES1); }
-// verify the n (<= 32) oldest of `waiting` candidates, one per lane
-__device__ __forceinline__ void verify_round(const drain_args &d, const uint32_t next_slot, const uint32_t waiting, const uint32_t n)
+// verify the n (<= 32) candidates from slot `head` on, one per lane
+__device__ __forceinline__ void verify_round(const drain_args &d, const uint32_t head, const uint32_t n)
 {
     const uint32_t lane = threadIdx.x & 31;
     if (lane < n) {
@@ -463,7 +463,7 @@ __device__ __forceinline__ void verify_round(const drain_args &d, const uint32_t
         const uint4 c0 = lds128(smem_sa() + UN_OFF_MISC + 4u * DC_SLOTS_A);
         const uint2 c1 = lds64(smem_sa() + UN_OFF_MISC + 4u * DC_ONE);
         pc.slots_a = c0.x; pc.shift_a = c0.y; pc.slots_b = c0.z; pc.shift_b = c0.w; pc.one = c1.x; pc.rec = c1.y;
-        const uint4 e = lds128v(warp_c_sa() + ((next_slot - waiting + lane) & (UN_CCAP - 1)) * UN_C_BYTES1);
+        const uint4 e = lds128v(warp_c_sa() + ((head + lane) & (UN_CCAP - 1)) * UN_C_BYTES1);
         const uint64_t pos = ((uint64_t)(e.w >> 8) << 32) | e.z;
         if (d.vtab_sa) verify_cand<true>(d, pc, e.x, e.y, e.w & 0xffu, pos);
         else verify_cand<false>(d, pc, e.x, e.y, e.w & 0xffu, pos);
@@ -478,10 +478,10 @@ __device__ __noinline__ void flush_candidates()
     d.vtab_sa = dc(DC_VTAB_SA);
     d.counts_sa = dc(DC_COUNTS_SA);
     __syncwarp();
-    const uint32_t cs = lds32v(d.scratch_sa + SC_CAND);
-    verify_round(d, cs >> 8, cs & 0xffu, cs & 0xffu); // fewer than 32 are waiting between resolve steps
+    const uint2 cs = lds64v(d.scratch_sa + SC_CAND); // {handed out, verified}: fewer than 32 apart between resolve steps
+    verify_round(d, cs.y, cs.x - cs.y);
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) sts32v(d.scratch_sa + SC_CAND, cs & ~0xffu);
+    if ((threadIdx.x & 31) == 0) sts32v(d.scratch_sa + SC_CAND + 4, cs.x);
     __syncwarp();
 }
 
@@ -656,40 +656,69 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
         }
         nextb = pe - gq > 255 ? 255u : pe - gq;
     }
-    // Phase 2.  Every lane appends its alive candidates to the warp's candidate ring, one per trip, and whenever 32 are
-    // waiting they are verified, one per lane -- whichever event they came from, this resolve step's or an earlier one's.
-    // (A candidate is self-contained: its first 8 bytes, its position, the bytes left in its packet.)
+    // Phase 2.  Every lane appends its alive candidates to the warp's candidate ring, and whenever 32 are waiting they are
+    // verified, one per lane -- whichever event they came from, this resolve step's or an earlier one's.  (A candidate is
+    // self-contained: its first 8 bytes, its position, the bytes left in its packet.)
     const uint64_t gpos = (((uint64_t)row0_hi << 32) | row0_lo) + gq; // absolute position of my group (a multiple of 32)
-    uint32_t cs = lds32v(d.scratch_sa + SC_CAND);                     // waiting | next slot << 8
-    const uint32_t c_sa = warp_c_sa();
     const uint32_t gpos_lo = (uint32_t)gpos, gpos_hi8 = (uint32_t)(gpos >> 32) << 8;
+    const uint32_t c_sa = warp_c_sa(), cst_sa = d.scratch_sa + SC_CAND;
     const bool walls = __any_sync(FULL, bm != 0); // some group of this step holds a packet boundary (C3: one step in two)
-    for (;;) {
-        const uint32_t any = __ballot_sync(FULL, am != 0);
-        if (any == 0) break;
-        if (am) {
-            const uint32_t i = __ffs(am) - 1;
-            am &= am - 1;
-            const uint32_t a = entry_sa + (i & ~3u), sh = 8u * (i & 3u);
-            const uint32_t w0 = lds32v(a), w1 = lds32v(a + 4), w2 = lds32v(a + 8); // i + 7 < 40: inside the event's text
-            uint32_t end = nextb; // the end of the candidate's packet: the first packet start after byte i
-            if (walls) {
-                const uint32_t above = bm & ~((2u << i) - 1u);
-                if (above) end = (uint32_t)__ffs(above) - 1u;
-            }
-            const uint32_t slot = ((cs >> 8) + __popc(any & lt)) & (UN_CCAP - 1);
-            sts128v(c_sa + slot * UN_C_BYTES1, __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
-                    gpos_lo | i, (end - i) | gpos_hi8);
+    // my first alive candidate goes to `slot`
+    auto push_one = [&](const uint32_t slot) {
+        const uint32_t i = __ffs(am) - 1;
+        am &= am - 1;
+        const uint32_t a = entry_sa + (i & ~3u), sh = 8u * (i & 3u);
+        const uint32_t w0 = lds32v(a), w1 = lds32v(a + 4), w2 = lds32v(a + 8); // i + 7 < 40: inside the event's text
+        uint32_t end = nextb; // the end of the candidate's packet: the first packet start after byte i
+        if (walls) {
+            const uint32_t above = bm & ~((2u << i) - 1u);
+            if (above) end = (uint32_t)__ffs(above) - 1u;
         }
-        cs += __popc(any) * 0x101u;
+        sts128v(c_sa + (slot & (UN_CCAP - 1)) * UN_C_BYTES1, __funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                gpos_lo | i, (end - i) | gpos_hi8);
+    };
+    const uint2 cs0 = lds64v(cst_sa); // {slots handed out, slots verified}; fewer than 32 candidates are waiting
+    uint32_t ctail = cs0.x, chead = cs0.y;
+    // every lane's run of slots: a prefix sum of the counts (a shared-memory atomic would serialise its 20-odd lanes on
+    // the pipe the filter's lookups need)
+    const uint32_t cnt = __popc(am);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (uint32_t dd = 1; dd < 32; dd <<= 1)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 v;\n\t"
+                     "shfl.sync.up.b32 v|p, %0, %1, 0, 0xffffffff;\n\t"
+                     "@p add.u32 %0, %0, v;\n\t}"
+                     : "+r"(incl)
+                     : "r"(dd));
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    if (ctail - chead + total <= UN_CCAP) {
+        // The ring takes them all: every lane fills its run at its own pace -- no trips in step with the lane that has
+        // the most.  (The order of the candidates in the ring does not matter.)
+        uint32_t slot = ctail + incl - cnt;
+        while (am) push_one(slot++);
+        ctail += total;
         __syncwarp();
-        if ((cs & 0xffu) >= 32u) {
-            verify_round(d, cs >> 8, cs & 0xffu, 32u);
-            cs -= 32u;
+    } else {
+        // (dense candidates: trips of at most one candidate per lane, verified as soon as 32 are waiting)
+        for (;;) {
+            const uint32_t any = __ballot_sync(FULL, am != 0);
+            if (any == 0) break;
+            if (am) push_one(ctail + __popc(any & lt));
+            ctail += __popc(any);
             __syncwarp();
+            if (ctail - chead >= 32u) {
+                verify_round(d, chead, 32u);
+                chead += 32u;
+                __syncwarp();
+            }
         }
     }
-    if (lane == 0) sts32v(d.scratch_sa + SC_CAND, cs);
+    while (ctail - chead >= 32u) {
+        verify_round(d, chead, 32u);
+        chead += 32u;
+    }
+    __syncwarp();
+    if (lane == 0) sts64v(cst_sa, ctail, chead);
     __syncwarp();
 }
 
