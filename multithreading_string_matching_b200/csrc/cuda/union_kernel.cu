@@ -494,17 +494,20 @@ __device__ __forceinline__ void drain_fetch(const uint32_t head, const uint32_t 
 {
     const uint32_t lane = threadIdx.x & 31;
     if (lane < n) {
-        const uint32_t tx = lds32v(warp_q_sa() + ((head + lane) & (UN_QCAP - 1)) * UN_Q_BYTES1);
+        const uint2 t = lds64v(warp_q_sa() + ((head + lane) & (UN_QCAP - 1)) * UN_Q_BYTES1);
+        const uint32_t tx = t.x;
         const uint32_t gq = (tx & 0x7fffffffu) << 5;
         const uint32_t set_sa = warp_scratch_sa() + ((tx >> 31) << 5); // the event's item
         const uint32_t e_rel = lds32v(set_sa + 12);
         const uint2 r0 = lds64v(set_sa + 16);
-        const bool in = gq < e_rel, more = in && gq + UN_GRP < ((e_rel + 31u) & ~31u);
+        // the lookahead matters to the last quarter's starts only (25..31: the re-run's bytes 32..35, a candidate's bytes
+        // up to 38); an LDGSTS is charged by the lane, so the other events' lanes sit this one out
+        const bool in = gq < e_rel, more = in && (t.y >> 24) != 0 && gq + UN_GRP < ((e_rel + 31u) & ~31u);
         const uint8_t *src = dc_ptr(DC_TEXT_LO) + (((uint64_t)r0.y << 32) | r0.x) + (in ? gq : 0u);
         const uint32_t dst = warp_t_sa() + lane * UN_T_BYTES1;
         cp_async16(dst, src, in ? 16u : 0u);
         cp_async16(dst + 16, src + 16, in ? 16u : 0u);
-        cp_async8(dst + 32, more ? src + 32 : src, more ? 8u : 0u);
+        if (more) cp_async8(dst + 32, src + 32, 8u);
     }
 }
 
