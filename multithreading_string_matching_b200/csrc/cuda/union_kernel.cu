@@ -556,7 +556,8 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
         while (quarters) {
             const uint32_t k8 = (__ffs(quarters) - 1) & ~7u; // 8k
             quarters &= quarters - 1;
-            const uint32_t w0 = lds32v(entry_sa + k8), w1 = lds32v(entry_sa + k8 + 4), w2 = lds32v(entry_sa + k8 + 8);
+            const uint2 w01 = lds64v(entry_sa + k8);
+            const uint32_t w0 = w01.x, w1 = w01.y, w2 = lds32v(entry_sa + k8 + 8);
             uint32_t S = 0, cmr = 0, zr = 0;
             // Two bytes per update, as in the row loop; after an update bits 24..28 / 18..22 hold the candidate buckets of
             // the start three before b0 / b1, bits 29 / 23 "that byte is NUL".  Adding 0x1f to a 5-bit field carries into
