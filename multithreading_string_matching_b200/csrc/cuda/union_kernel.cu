@@ -34,21 +34,28 @@
 //  row loop, the ONE place the resolve step is inlined (a call from inside the loop made ptxas spill five of the
 //  loop's values around it; the item switch and the final flush call a not-inlined copy) -- resolves the 32 oldest
 //  at once, in stream order, one per lane:
-//  Phase 0 (issued one trip of the row loop earlier, cp.async: nobody waits for L2): the lane's event's group (32 B
-//  + 8 B lookahead) travels into the warp's staging area.
+//  Phase 0 (issued one trip of the row loop earlier, cp.async: nobody waits for L2): the lane's event's group (32 B,
+//  and 8 B of lookahead when its last quarter reported) travels into the warp's staging area.  (One bulk copy -- TMA --
+//  per event completing on a per-warp mbarrier was measured in its place: 13 % slower, 48-byte copies are not what that
+//  engine is for.)
 //  Phase 1:
-//    - the lane re-runs the filter over the quarter that reported, this time recording which start positions
-//      fired and which bytes are NUL;
-//    - it finds the packet that holds its first candidate in its item's slice of `offsets` (interpolation
-//      guess, then binary search); the item's packet and byte range waits in the warp's scratch words;
+//    - the lane re-runs the filter over the quarter that reported (two bytes per update, like the row loop), this time
+//      recording which start positions fired and which bytes are NUL;
+//    - it finds the packet that holds its first candidate: a division when all the item's packets have the same size,
+//      else a search in the item's slice of `offsets` (interpolation guess, then binary search); the item's packet and
+//      byte range waits in the warp's scratch words;
 //    - a candidate start q in packet [ps, pe) is alive when no NUL lies in [ps, q) -- the reference's
 //      "text ends at the first NUL" rule (serial.c:191).  NULs inside the quarter come from the lane's own
 //      mask; the last NUL before it comes from the nearest earlier event that held one (events are in
 //      stream order, every NUL byte of the stream raises one) or from the warp's carry.
-//  Phase 2, every lane its own alive candidates: the candidate's first bytes select one slot in each of the two
-//  probe tables of automaton.c (two-byte patterns by their two bytes, longer ones by their first three), the
-//  slots' pattern records (first 8 bytes + masks, length, id) are compared, longer patterns word by word, and a
-//  hit is counted when it ends inside its packet (q + len <= pe).
+//  Phase 2: every lane appends its alive candidates -- first 8 text bytes, absolute position, bytes left in the packet:
+//  16 bytes, self-contained -- to the warp's CANDIDATE RING, at its own pace (slot runs from a prefix sum of the counts).
+//  Whenever 32 candidates are waiting, whichever resolve step they came from, they are verified one per lane: the
+//  candidate's first bytes select one slot in each of the two probe tables of automaton.c (two-byte patterns by their
+//  two bytes, longer ones by their first three), the slots' pattern records (first 8 bytes + masks, length, id) are
+//  compared, longer patterns word by word against the text in global memory, and a hit is counted when it ends inside
+//  its packet (q + len <= pe).  Every verification round runs with all 32 lanes busy; what is left at the end of the
+//  batch is flushed.
 //  So every pattern occurrence that lies inside one packet and has no NUL before it in that packet is
 //  counted exactly once.  Counts go to shared-memory counters and leave the block as one atomic per
 //  distinct pattern.  No separators, no padding and no second pass over the payload.
