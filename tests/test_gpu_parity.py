@@ -300,6 +300,30 @@ def test_nul_dense_payloads(matchers, oracle):
     check_all(matchers, oracle, pats, pkts * 7, label="sandwich")
 
 
+def test_candidate_ring_dense_sparse_and_long(matchers, oracle):
+    """The union engine's candidate ring (union_kernel.cu, phase 2 of the resolve step): candidates wait across resolve
+    steps until 32 have come together.  Dense candidates -- every byte starts a pattern, more per step than the ring
+    holds, so the step falls back to trips of 32 --, a few candidates that are only flushed at the end of the batch,
+    and patterns of more than 8 bytes, whose tail is compared against the text in global memory, at every offset of a
+    group, across groups, rows and the end of the batch."""
+    rng = random.Random(5)
+    dense = [b"a", b"aa", b"aaaa", b"aaaaaaaaa", b"ab", b"ba"]
+    pkts = [b"a" * rng.randint(0, 700) for _ in range(60)] + [b"ab" * 300, b"a" * 31 + b"\0" + b"a" * 99, b"a" * 5000]
+    check_all(matchers, oracle, dense, pkts, label="dense")
+    check_all(matchers, oracle, dense, [b"a" * 100_000] * 3, engines=["union"], label="dense, many rows")
+    sparse = [b"needle", b"http_decode"]
+    check_all(matchers, oracle, sparse, [b"x" * 3000 + b"needle" + b"y" * 2000, b"z" * 100, b"http_decode"], label="sparse")
+    long_pats = [b"content-list", b"ignorehosts12345678901234567890", b"0123456789abcdef0123456789abcdef0123456789abcdef0123456789abcdefXYZ"]
+    pkts = []
+    for p in long_pats:
+        for lead in range(0, 70):
+            pkts.append(b"." * lead + p)                      # ends with the packet (and once with the batch)
+            pkts.append(b"." * lead + p[:-1])                 # one byte short
+            pkts.append(b"." * lead + p + b"." * (lead % 5))
+    rng.shuffle(pkts)
+    check_all(matchers, oracle, long_pats, pkts + [long_pats[2]], label="long")
+
+
 # ---- synthetic workloads of BASELINE.json ------------------------------------------------------
 
 def test_synthetic_device_resident_stream(matchers, oracle, strings):
