@@ -107,6 +107,7 @@ int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets
                     uint64_t *counts_out);
 
 /* Device form: d_bytes (32-byte aligned, readable up to total_bytes rounded up to 32) and d_offsets
+ * (values below 2^56, at most 64 GiB between the first and the last: KMPB_ELIMIT otherwise)
  * are device memory on the context's GPU; d_counts[n_pat] (device, uint64) is ACCUMULATED into, so
  * a caller can sum several batches and all-reduce once (mpi_dumping.c:202).  Asynchronous on
  * `stream` (a cudaStream_t passed as void*; NULL = CUDA's default stream, as in the runtime API).
