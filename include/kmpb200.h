@@ -202,6 +202,11 @@ uint64_t kmpb_pcap_packets(const kmpb_pcap *pc); /* frames whose payload the ext
 uint64_t kmpb_pcap_frames(const kmpb_pcap *pc);  /* records in the file */
 uint64_t kmpb_pcap_bytes(const kmpb_pcap *pc);   /* sum of the accepted payload lengths */
 int kmpb_count_pcap(kmpb_ctx *ctx, const kmpb_pcap *pc, uint64_t first, uint64_t count, uint64_t *counts_out);
+/* Optional: allocate the device and pinned host staging buffers of the chunked forms (kmpb_count_host, kmpb_count_pcap,
+ * kmpb_stream_*) ahead of time, for batches of up to max_batch_bytes payload bytes and max_packets packets (0, 0: the
+ * defaults of kmpb_count_pcap) -- e.g. while another thread is still reading the savefile (serial.c:91-141); pinned
+ * allocations take a few hundred milliseconds.  The counting calls grow the buffers themselves when they must. */
+int kmpb_reserve_staging(kmpb_ctx *ctx, uint64_t max_batch_bytes, uint64_t max_packets);
 
 /* Frames arriving one at a time (live_openmp_task.c:160-217: pcap_next in a loop, batches handed to
  * tasks while the capture goes on).  kmpb_stream_push runs the extractor on one captured frame and

@@ -458,6 +458,18 @@ int kmpb_count_host(kmpb_ctx *ctx, const uint8_t *bytes, const uint64_t *offsets
 // Streamed savefile path: pack a chunk of payloads into a pinned staging slot (all host threads), copy
 // it to the slot's device twin and match it on the slot's stream while the next chunk is packed -- the
 // producer/consumer shape of openmp_task.c:113-178 with the GPU as the consumer.
+int kmpb_reserve_staging(kmpb_ctx *ctx, uint64_t max_batch_bytes, uint64_t max_packets)
+{
+    if (ctx == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL argument");
+    if (max_batch_bytes == 0) max_batch_bytes = (64ull << 20) + 65536; // a ~64 MiB batch of whole packets
+    if (max_packets == 0) max_packets = 1ull << 20;
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_staging(ctx, max_batch_bytes, max_packets))) return rc;
+    if ((rc = ensure_host_staging(ctx, max_batch_bytes, max_packets))) return rc;
+    return kmpb_union_scratch(ctx, max_batch_bytes);
+}
+
 int kmpb_count_pcap(kmpb_ctx *ctx, const kmpb_pcap *pc, uint64_t first, uint64_t count, uint64_t *counts_out)
 {
     if (ctx == nullptr || pc == nullptr) return kmpb_fail(KMPB_EINVAL, "NULL argument");

@@ -48,6 +48,7 @@ typedef struct {
     double start;
     int rc;
     char err[512];
+    kmpb_ctx *ctx; /* kept until the report is out: freeing pinned buffers is not part of the answer */
 } shard_job;
 
 /* One host thread per GPU: the context and the pattern tables are built while the main thread frames
@@ -58,8 +59,9 @@ static void *run_shard(void *arg)
     kmpb_ctx *ctx = NULL;
     job->rc = kmpb_create(&ctx, job->device);
     if (job->rc == 0) job->rc = kmpb_set_patterns(ctx, job->pats->blob, job->pats->pat_off, job->pats->n_pat);
+    if (job->rc == 0) job->rc = kmpb_reserve_staging(ctx, 0, 0); /* pinned staging, while the main thread frames the savefile */
     if (job->rc != 0) snprintf(job->err, sizeof job->err, "%s", kmpb_last_error());
-    if (getenv("KMPB_STATS")) fprintf(stderr, "kmp_match: GPU %d context and pattern tables ready %.3f s after start\n", job->device, now_seconds() - job->start);
+    if (getenv("KMPB_STATS")) fprintf(stderr, "kmp_match: GPU %d context, pattern tables and staging buffers ready %.3f s after start\n", job->device, now_seconds() - job->start);
     pthread_mutex_lock(&job->gate->lock);
     while (!job->gate->done) pthread_cond_wait(&job->gate->ready, &job->gate->lock);
     const kmpb_pcap *pc = job->gate->pc;
@@ -70,7 +72,7 @@ static void *run_shard(void *arg)
         job->rc = kmpb_count_pcap(ctx, pc, first, count, job->counts);
         if (job->rc != 0) snprintf(job->err, sizeof job->err, "%s", kmpb_last_error());
     }
-    kmpb_destroy(ctx);
+    job->ctx = ctx;
     return NULL;
 }
 
@@ -170,7 +172,10 @@ int main(int argc, char **argv)
                 (unsigned long long)kmpb_pcap_bytes(pc), pats.n_pat, n_gpus,
                 (double)kmpb_pcap_bytes(pc) / s / 1e9, (double)kmpb_pcap_packets(pc) / s / 1e6);
     }
-    for (int g = 0; g < n_gpus; g++) free(jobs[g].counts);
+    for (int g = 0; g < n_gpus; g++) {
+        kmpb_destroy(jobs[g].ctx);
+        free(jobs[g].counts);
+    }
     free(jobs);
     free(threads);
     free(counts);
