@@ -98,7 +98,7 @@ constexpr uint32_t UN_Q_BYTES1 = 8; // an event in the ring: group index | item 
 constexpr uint32_t UN_T_WORDS = 12; // an event being resolved: 32 B group, 8 B lookahead, group index | parity, packet boundaries in the group
 constexpr uint32_t UN_T_BYTES1 = UN_T_WORDS * 4;
 #ifndef KMPB_UN_DENSE
-#define KMPB_UN_DENSE 8
+#define KMPB_UN_DENSE 12
 #endif
 constexpr uint32_t UN_DENSE = KMPB_UN_DENSE; // reporting groups per row from which superseded NUL-only events are dropped (> 32: never)
 constexpr uint32_t UN_LUT_BYTES = 256 * 128; // one table: a 128-byte row (32 lanes x 4 bytes) per byte value
