@@ -317,13 +317,15 @@ __device__ __forceinline__ uint32_t lds8v(uint32_t saddr)
 }
 __device__ __forceinline__ uint32_t saddr_of(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// bits [lo, hi) of a 32-bit word, 0 <= lo, hi <= 32
-__device__ __forceinline__ uint32_t bit_window(uint32_t lo, uint32_t hi)
+// bits [0, x) of a 32-bit word, 0 <= x <= 32 (PTX shl clamps a shift amount above 31 to 32: 1 << 32 is 0, minus 1 all ones)
+__device__ __forceinline__ uint32_t bits_below(uint32_t x)
 {
-    const uint32_t below_hi = hi >= 32 ? FULL : (1u << hi) - 1u;
-    const uint32_t below_lo = lo >= 32 ? FULL : (1u << lo) - 1u;
-    return below_hi & ~below_lo;
+    uint32_t r;
+    asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(x));
+    return r - 1u;
 }
+// bits [lo, hi) of a 32-bit word, 0 <= lo, hi <= 32
+__device__ __forceinline__ uint32_t bit_window(uint32_t lo, uint32_t hi) { return bits_below(hi) & ~bits_below(lo); }
 // x clamped to 0..32, x signed
 __device__ __forceinline__ uint32_t clamp32(int32_t x) { return (uint32_t)min(max(x, 0), 32); }
 
@@ -588,7 +590,7 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
         // past e_rel may be anything, so NULs count below e_rel only
         const uint32_t lo = clamp32((int32_t)b_rel - (int32_t)gq), hi = clamp32((int32_t)e_rel - (int32_t)gq);
         cm &= bit_window(lo, hi);
-        zm &= bit_window(0, hi);
+        zm &= bits_below(hi);
     }
     // last NUL before my event's bytes: the nearest earlier event of the same item that holds one, else the carry of
     // my item (the events of an item are in stream order; those of the older item come first)
@@ -598,15 +600,12 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
     const uint32_t below = mine & lt;
     const uint32_t from_below = __shfl_sync(FULL, mylast1, below ? 31 - __clz(below) : 0);
     const uint32_t prev1 = below ? from_below : carry;
-    // the carries: the last NUL of either item among these events
-    const uint32_t top0 = nulm & ~parm, top1 = nulm & parm;
-    const uint32_t new0 = __shfl_sync(FULL, mylast1, top0 ? 31 - __clz(top0) : 0);
-    const uint32_t new1 = __shfl_sync(FULL, mylast1, top1 ? 31 - __clz(top1) : 0);
+    // the carries: the last NUL of either item among these events is stored by the lane that holds it -- the one with
+    // a NUL and no lane of its item with a NUL above it
+    uint32_t gt;
+    asm("mov.u32 %0, %%lanemask_gt;" : "=r"(gt));
     __syncwarp();
-    if (lane == 0) {
-        if (top0) sts32v(d.scratch_sa + 24, new0);
-        if (top1) sts32v(d.scratch_sa + 32 + 24, new1);
-    }
+    if (zm && !(mine & gt)) sts32v(d.scratch_sa + (par << 5) + 24, mylast1);
 
     uint32_t am = 0, bm = 0, nextb = 255; // alive candidates; packet starts inside the group (bit = offset);
                                           // offset of the first packet start at or after the group's end
