@@ -349,7 +349,7 @@ enum { DC_TEXT_LO = 0, DC_TEXT_HI,   // p.bytes - p.abs_base: absolute byte 0
        DC_LAST = 31 };           // "I am the last block" flag
 
 // The scratch words of a warp (128 bytes): two sets of 32 bytes, one per item parity --
-//   {ks, ke, b_rel, e_rel, row0 lo, row0 hi, carry, packet size}: the item's packets [ks, ke), its bytes
+//   {ks (or 1 / L as a float when all packets have L bytes), ke, b_rel, e_rel, row0 lo, row0 hi, carry, packet size}: the item's packets [ks, ke), its bytes
 //   [b_rel, e_rel) relative to row0 = the absolute position of its first row, 1 + the (relative) position of the last
 //   NUL byte among its events resolved so far (0: none), and either 0x80000000 | L when all its packets have L bytes or
 //   (ke - ks) / (e_rel - b_rel) as a float (the interpolation guess of the packet lookup) --
@@ -622,11 +622,12 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
         uint32_t k, ps, pe;
         if (uniform) {
             const uint32_t x = p0 - b_rel;
-            uint32_t q = (uint32_t)((float)x * __frcp_rn((float)L)); // x < 2^24 or the quotient is small: off by one at most
+            // (1 / L waits in the set's first word -- a uniform item has no use for its first packet's index)
+            const uint32_t q = (uint32_t)((float)x * __uint_as_float(ks)); // x < 2^24 or the quotient is small: off by one at most
             int32_t r = (int32_t)(x - q * L);
-            if (r < 0) { q--; r += (int32_t)L; }
-            if (r >= (int32_t)L) { q++; r -= (int32_t)L; }
-            k = ks + q;
+            if (r < 0) r += (int32_t)L;
+            if (r >= (int32_t)L) r -= (int32_t)L;
+            k = 0;
             ps = p0 - (uint32_t)r;
             pe = ps + L;
         } else {
@@ -657,7 +658,7 @@ __device__ __forceinline__ void drain_body(const uint32_t head, const uint32_t n
             if (!dead) am |= cm & seg & (z ? (z & (0u - z)) - 1u : FULL); // starts before the packet's first NUL
             if (b == 32) break;
             bm |= 1u << b;          // the next packet starts inside my group
-            if (k + 1 >= ke) break; // ... or the item ends there: nothing beyond is mine
+            if (pe >= e_rel) break; // ... or the item ends there (what may follow are empty packets): nothing beyond is mine
             a = b;
             dead = false;
             k++;
@@ -843,17 +844,18 @@ __global__ void __launch_bounds__(UN_THREADS, 1) kmpb_union_kernel(const __grid_
         const uint64_t row0 = b_abs & ~127ull; // absolute position of the item's first row
         const uint32_t b_rel = (uint32_t)(b_abs - row0), e_rel = (uint32_t)(e_abs - row0);
         // do all the item's packets have the same size?  (fixed-size records: the packet lookup becomes a division)
-        uint32_t psize;
+        uint32_t psize, word0 = ks;
         {
             const uint64_t L = uni(p.offsets[ks + 1]) - b_abs;
             bool same = L != 0 && L * (ke - ks) == e_abs - b_abs;
             for (uint32_t j = lane + 1; same && j < ke - ks; j += 32) same = p.offsets[ks + j] == b_abs + j * L;
             same = __all_sync(FULL, same);
             psize = same ? 0x80000000u | (uint32_t)L : __float_as_uint((float)(ke - ks) / (float)(e_rel - b_rel));
+            if (same) word0 = __float_as_uint(__frcp_rn((float)(uint32_t)L)); // the packet lookup of such an item is a multiplication
         }
         if (lane == 0) {
             const uint32_t set_sa = warp_scratch_sa() + (par << 5);
-            sts128v(set_sa, ks, ke, b_rel, e_rel);
+            sts128v(set_sa, word0, ke, b_rel, e_rel);
             sts128v(set_sa + 16, (uint32_t)row0, (uint32_t)(row0 >> 32), 0u, psize);
             sts64v(warp_scratch_sa() + SC_STATE, par, pending());
         }
